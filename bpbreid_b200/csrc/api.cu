@@ -1,0 +1,197 @@
+// C ABI shim (include/bpbreid_sm100.h) + error plumbing + tensor-map encoding.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bpbreid_sm100.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bpb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+    return 1;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess || p == nullptr) {
+            set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                    CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return 1;
+    cuuint64_t d[5], s[5];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides[i]; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    const CUresult r = fn(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, s, b, e,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u] "
+                  "estride=[%u,%u,%u,%u] base=%p",
+                  static_cast<int>(r), rank, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0),
+                  (unsigned long long)(rank > 2 ? d[2] : 0), (unsigned long long)(rank > 3 ? d[3] : 0), b[0],
+                  rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0, rank > 3 ? b[3] : 0, e[0], rank > 1 ? e[1] : 0,
+                  rank > 2 ? e[2] : 0, rank > 3 ? e[3] : 0, base);
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace bpb
+
+using namespace bpb;
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+const char* bpb_last_error(void) { return g_err; }
+int bpb_abi_version(void) { return 1; }
+
+int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
+                  int ksize, int stride, int bn_hint, void* stream) {
+    return conv_bf16_tc(x, w, y, stats, n, h, wd, cin, cout, ksize, stride, bn_hint, S(stream));
+}
+int bpb_conv_num_mtiles(int n, int ho, int wo) { return conv_num_mtiles(n, ho, wo); }
+int bpb_conv_ref_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize,
+                      int stride, void* stream) {
+    return conv_ref(x, w, y, n, h, wd, cin, cout, ksize, stride, S(stream));
+}
+int bpb_stem_conv(const float* img, const float* w, void* y, int n, int h, int wd, int cout, int ksize, int stride,
+                  void* stream) {
+    return stem_conv(img, w, y, n, h, wd, cout, ksize, stride, S(stream));
+}
+int bpb_colstats_bf16(const void* x, float* partials, int m, int c, void* stream) {
+    return colstats_bf16(x, partials, m, c, nullptr, S(stream));
+}
+int bpb_colstats_tiles(int m) { return colstats_tiles(m); }
+int bpb_bn_finalize(const float* partials, int tiles, int c, int c_lo, int64_t count, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    float* scale, float* shift, void* stream) {
+    return bn_finalize(partials, tiles, c, c_lo, count, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                       shift, S(stream));
+}
+int bpb_bn_eval_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                     float eps, int c, float* scale, float* shift, void* stream) {
+    return bn_eval_fold(gamma, beta, running_mean, running_var, eps, c, scale, shift, S(stream));
+}
+int bpb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* res_scale,
+                 const float* res_shift, void* y, int64_t m, int c, int relu, void* stream) {
+    return bn_apply(x, scale, shift, res, res_scale, res_shift, y, m, c, relu, S(stream));
+}
+int bpb_fuse_sum(const void* const* srcs, const float* const* scales, const float* const* shifts,
+                 const int* shifts_log2, int nsrc, void* y, int n, int h, int wd, int c, int relu, void* stream) {
+    return fuse_sum(srcs, scales, shifts, shifts_log2, nsrc, y, n, h, wd, c, relu, S(stream));
+}
+int bpb_upsample_concat(const void* const* srcs, const int* chans, const int* hs, const int* ws, int nsrc, void* y,
+                        int n, int h, int wd, void* stream) {
+    return upsample_concat(srcs, chans, hs, ws, nsrc, y, n, h, wd, S(stream));
+}
+int bpb_maxpool3x3s2(const void* x, void* y, int n, int h, int wd, int c, int pad, int ceil_mode, void* stream) {
+    return maxpool3x3s2(x, y, n, h, wd, c, pad, ceil_mode, S(stream));
+}
+int bpb_instnorm_stats(const void* x, float* mean_rstd, int n, int hw, int c, int c_lo, int c_hi, float eps,
+                       void* stream) {
+    return instnorm_stats(x, mean_rstd, n, hw, c, c_lo, c_hi, eps, S(stream));
+}
+int bpb_ibn_apply(const void* x, const float* in_mean_rstd, const float* in_gamma, const float* in_beta,
+                  const float* bn_scale, const float* bn_shift, void* y, int n, int hw, int c, int half, int relu,
+                  void* stream) {
+    return ibn_apply(x, in_mean_rstd, in_gamma, in_beta, bn_scale, bn_shift, y, n, hw, c, half, relu, S(stream));
+}
+
+int bpb_pixel_fold(const float* w, const float* b, const float* scale, const float* shift, int kp1, int c, float* wf,
+                   float* bf, void* stream) {
+    return pixel_fold(w, b, scale, shift, kp1, c, wf, bf, S(stream));
+}
+int bpb_pixel_classify(const void* feats, const float* wf, const float* bf, int n, int hw, int c, int kp1,
+                       float* logits_nchw, float* probs, float* fg_mask, int* vis_bits, float* vis_cont,
+                       void* stream) {
+    return pixel_classify(feats, wf, bf, n, hw, c, kp1, logits_nchw, probs, fg_mask, vis_bits, vis_cont, S(stream));
+}
+int bpb_part_pool(const void* feats, const float* probs, const float* fg_mask, int n, int hw, int c, int kp1,
+                  float* pooled, void* stream) {
+    return part_pool(feats, probs, fg_mask, n, hw, c, kp1, pooled, S(stream));
+}
+int bpb_linear_tf32(const float* a, int64_t lda, const float* w, const float* bias, float* out, int m, int n, int k,
+                    int ldo, int a_mode, int a_parts, void* stream) {
+    return linear_tf32_tc(a, lda, w, bias, out, m, n, k, ldo, a_mode, a_parts, S(stream));
+}
+int bpb_bn1d(const float* x, const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+             float* running_var, float* y, int m, int c, int relu, int training, void* stream) {
+    return bn1d_train(x, gamma, beta, eps, momentum, running_mean, running_var, y, m, c, relu, training, S(stream));
+}
+
+int bpb_vis_unpack(const int* vis_bits, const float* vis_cont, int n, int kp1, uint8_t* out_b, float* out_f,
+                   void* stream) {
+    return vis_unpack(vis_bits, vis_cont, n, kp1, out_b, out_f, S(stream));
+}
+int bpb_weighted_sum(const float* const* terms, const float* weights, int n, float* out, void* stream) {
+    return weighted_sum(terms, weights, n, out, S(stream));
+}
+
+int bpb_triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
+                    float margin, float* dist_nn, float* hp, float* hn, int* hp_idx, int* hn_idx, float* out4,
+                    void* stream) {
+    return triplet_fwd(emb_knd, labels, vis, vis_mode, n, k, d, margin, dist_nn, hp, hn, hp_idx, hn_idx, out4,
+                       S(stream));
+}
+int bpb_ce_ls_fwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c,
+                  float eps, float* scratch, float* out2, void* stream) {
+    return ce_ls_fwd(logits, ld, targets, weights, n, c, eps, scratch, out2, S(stream));
+}
+int bpb_pixel_ce_fwd(const float* logits_nchw, const float* target_masks, int n, int kp1, int hf, int wf, int hm,
+                     int wm, float label_smoothing, float* partial, float* out2, void* stream) {
+    return pixel_ce_fwd(logits_nchw, target_masks, n, kp1, hf, wf, hm, wm, label_smoothing, partial, out2, S(stream));
+}
+
+int bpb_part_distance(const float* qf, const float* gf, const void* qv, const void* gv, int vis_mode, int nq, int ng,
+                      int p, int d, int metric, int strat, int impl, float* dist, float* part_dist, float* scratch,
+                      void* stream) {
+    return part_distance(qf, gf, qv, gv, vis_mode, nq, ng, p, d, metric, strat, impl, dist, part_dist, scratch,
+                         S(stream));
+}
+int64_t bpb_part_distance_scratch_floats(int nq, int ng, int p) {
+    return 4 + static_cast<int64_t>(p) * (static_cast<int64_t>(nq) + ng);
+}
+int bpb_rank_market1501(const float* dist, const int64_t* q_pids, const int64_t* g_pids, const int64_t* q_camids,
+                        const int64_t* g_camids, int nq, int ng, int max_rank, double* ap64, float* ap32,
+                        int* first_rank, float* cmc, double* map_out, int64_t* num_valid, float* map32_out,
+                        int* overflow_flag, void* stream) {
+    return rank_market1501(dist, q_pids, g_pids, q_camids, g_camids, nq, ng, max_rank, ap64, ap32, first_rank, cmc,
+                           map_out, num_valid, map32_out, overflow_flag, S(stream));
+}
+int bpb_argsort_rows(const float* dist, int nq, int ng, int32_t* indices, void* stream) {
+    return argsort_rows(dist, nq, ng, indices, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,404 @@
+// tcgen05 implicit-GEMM convolution / dense contraction for sm_100a.
+//
+//   D[128 x BN] (TMEM, fp32)  +=  A[128 x KC] (smem, TMA-staged)  *  B[BN x KC]^T (smem, TMA-staged)
+//
+// A is either an NHWC bf16 activation tensor read through a 4-D tensor map (c, w, h, n): one TMA box per
+// filter tap and channel chunk lands directly in the canonical K-major swizzled layout the tensor core
+// wants (row = output pixel, 128 or 64 bytes of channels per row); zero padding comes from TMA
+// out-of-bounds fill and stride-2 convolutions from the map's element strides -- or a plain row-major
+// matrix [M, K] (bf16, or fp32 consumed as tf32).  B is the weight matrix [Cout, taps*Cin], K-major.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> smem tile -> coalesced global stores + BN partial sums).
+// Reference semantics replaced: nn.Conv2d / nn.Linear call sites of torchreid/models/hrnet.py:67-137,
+// 211-257,449-483, torchreid/models/resnet.py:105-154, torchreid/models/bpbreid.py:324-350,398-415.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bpb {
+
+constexpr int kTileM = 128;
+constexpr int kNumThreads = 192;
+
+struct GemmParams {
+    int M;          // valid output rows (pixels)
+    int N;          // valid output columns (Cout)
+    int k_iters;    // taps * kchunks
+    int kchunks;    // channel chunks per tap
+    int kc;         // elements per chunk (row_bytes / elem size)
+    int cin;        // channels per tap (column offset of a tap inside B)
+    int row_bytes;  // 128 or 64: TMA inner box bytes == swizzle span
+    int stages;
+    int mode;       // 0: conv (4-D A map)   1: matrix (2-D A map)   2: part-concat matrix (3-D A map [parts, M, D])
+    int dchunks;    // mode 2: K chunks per part
+    int ksize, stride, pad, Ho, Wo;
+    int ldo;        // output leading dimension (elements)
+    void* out;
+    float* stats;   // [m_tiles, 2, N] per-tile column sum / sum of squares (EPI_RAW_STATS)
+    const float* bias;
+};
+
+enum Epi { EPI_RAW_STATS = 0, EPI_F32_BIAS = 1 };
+
+template <int BN, bool kTf32, int kEpi>
+__global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+    const int a_bytes = kTileM * p.row_bytes;
+    const int b_bytes = BN * p.row_bytes;
+    const int stage_bytes = a_bytes + b_bytes;
+
+    __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float red_smem[2][4][BN < 64 ? 64 : BN];   // [sum|sq][group][col] (only first 128/(BN/2) groups used)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc<BN>(&tmem_base_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            int n0 = 0, h0 = 0;
+            if (p.mode == 0) {
+                const int hw = p.Ho * p.Wo;
+                const int p0 = m_tile * kTileM;
+                n0 = p0 / hw;
+                h0 = (p0 % hw) / p.Wo;
+            }
+            for (int it = 0; it < p.k_iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t round = it / p.stages;
+                mbar_wait(&empty_bar[s], (round & 1) ^ 1);
+                uint8_t* a_dst = smem + s * stage_bytes;
+                uint8_t* b_dst = a_dst + a_bytes;
+                mbar_expect_tx(&full_bar[s], stage_bytes);
+                const int tap = it / p.kchunks, kcidx = it % p.kchunks;
+                if (p.mode == 0) {
+                    const int r = tap / p.ksize, sx = tap % p.ksize;
+                    tma_load_4d(a_dst, &tmA, &full_bar[s], kcidx * p.kc, sx - p.pad, h0 * p.stride + r - p.pad, n0);
+                } else if (p.mode == 1) {
+                    tma_load_2d(a_dst, &tmA, &full_bar[s], kcidx * p.kc, m_tile * kTileM);
+                } else {
+                    tma_load_3d(a_dst, &tmA, &full_bar[s], (kcidx % p.dchunks) * p.kc, m_tile * kTileM,
+                                kcidx / p.dchunks);
+                }
+                tma_load_2d(b_dst, &tmB, &full_bar[s], tap * p.cin + kcidx * p.kc, n_tile * BN);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        constexpr uint32_t idesc = make_idesc(kTf32, kTileM, BN);
+        const int k_per_instr_bytes = 32;                    // 16 bf16 or 8 tf32
+        const int instrs = p.row_bytes / k_per_instr_bytes;
+        for (int it = 0; it < p.k_iters; ++it) {
+            const int s = it % p.stages;
+            const uint32_t round = it / p.stages;
+            mbar_wait(&full_bar[s], round & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+                const uint64_t da = make_kmajor_desc(a_addr, p.row_bytes);
+                const uint64_t db = make_kmajor_desc(b_addr, p.row_bytes);
+                for (int k = 0; k < instrs; ++k) {
+                    const uint64_t adv = static_cast<uint64_t>((k * k_per_instr_bytes) >> 4);
+                    umma<kTf32>(tmem_base, da + adv, db + adv, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);                  // smem slot free once these MMAs retire
+                if (it == p.k_iters - 1) umma_commit(&tmem_full_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------ epilogue (warps 2..5) ------------------------------
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;          // row of the tile == output pixel
+        const int et = (warp - 2) * 32 + lane;  // 0..127 epilogue thread id
+        const int m0 = m_tile * kTileM, c_base = n_tile * BN;
+        const int valid_rows = min(kTileM, p.M - m0);
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+        if constexpr (kEpi == EPI_F32_BIAS) {
+            float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+                if (row < valid_rows) {
+                    float* dst = out + static_cast<size_t>(m0 + row) * p.ldo + c_base + c0;
+                    if (c_base + c0 + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o;
+                            o.x = __uint_as_float(v[j + 0]) + (p.bias ? p.bias[c_base + c0 + j + 0] : 0.f);
+                            o.y = __uint_as_float(v[j + 1]) + (p.bias ? p.bias[c_base + c0 + j + 1] : 0.f);
+                            o.z = __uint_as_float(v[j + 2]) + (p.bias ? p.bias[c_base + c0 + j + 2] : 0.f);
+                            o.w = __uint_as_float(v[j + 3]) + (p.bias ? p.bias[c_base + c0 + j + 3] : 0.f);
+                            *reinterpret_cast<float4*>(dst + j) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c_base + c0 + j < p.N)
+                                dst[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[c_base + c0 + j] : 0.f);
+                    }
+                }
+            }
+        } else {
+            // bf16 tile staged in (now idle) pipeline smem: [128][BN] with a 16-byte row pad
+            constexpr int kPitch = BN * 2 + 16;
+            uint8_t* tile = smem;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+                uint4* dst = reinterpret_cast<uint4*>(tile + row * kPitch + c0 * 2);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                    o.y = pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                    o.z = pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                    o.w = pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                    dst[j] = o;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // ---- per-tile column statistics from the bf16-rounded values ----
+            constexpr int kPairs = BN / 2;
+            constexpr int kGroups = (128 / kPairs) < 1 ? 1 : (128 / kPairs);   // BN=32:8, 64:4, 128:2, 256:1
+            if (p.stats != nullptr) {
+                // BN==256: 128 threads each own one channel pair over all rows
+                const int pair = et % kPairs, g = et / kPairs;
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                for (int r = g; r < valid_rows; r += kGroups) {
+                    const uint32_t u = *reinterpret_cast<const uint32_t*>(tile + r * kPitch + pair * 4);
+                    const float a = bf16_lo(u), b = bf16_hi(u);
+                    s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+                }
+                if constexpr (kGroups > 4) {
+                    // fold groups g and g+4 first (8 -> 4) through shuffles is not layout friendly; use smem twice
+                    __shared__ float red2[2][8][32];
+                    red2[0][g][pair * 2 + 0] = s0; red2[0][g][pair * 2 + 1] = s1;
+                    red2[1][g][pair * 2 + 0] = q0; red2[1][g][pair * 2 + 1] = q1;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (et < BN) {
+                        float s = 0.f, qq = 0.f;
+#pragma unroll
+                        for (int gg = 0; gg < 8; ++gg) { s += red2[0][gg][et]; qq += red2[1][gg][et]; }
+                        float* st = p.stats + static_cast<size_t>(m_tile) * 2 * p.N;
+                        st[c_base + et] = s;
+                        st[p.N + c_base + et] = qq;
+                    }
+                } else {
+                    red_smem[0][g][pair * 2 + 0] = s0; red_smem[0][g][pair * 2 + 1] = s1;
+                    red_smem[1][g][pair * 2 + 0] = q0; red_smem[1][g][pair * 2 + 1] = q1;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    for (int c = et; c < BN; c += 128) {
+                        float s = 0.f, qq = 0.f;
+#pragma unroll
+                        for (int gg = 0; gg < kGroups; ++gg) { s += red_smem[0][gg][c]; qq += red_smem[1][gg][c]; }
+                        float* st = p.stats + static_cast<size_t>(m_tile) * 2 * p.N;
+                        st[c_base + c] = s;
+                        st[p.N + c_base + c] = qq;
+                    }
+                }
+            }
+            // ---- coalesced 16-byte stores of the tile ----
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+            constexpr int kChunksPerRow = BN / 8;
+            for (int ch = et; ch < kTileM * kChunksPerRow; ch += 128) {
+                const int r = ch / kChunksPerRow, cc = ch % kChunksPerRow;
+                if (r < valid_rows) {
+                    const uint4 o = *reinterpret_cast<const uint4*>(tile + r * kPitch + cc * 16);
+                    *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + r) * p.ldo + c_base + cc * 8) = o;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+template <int BN, bool kTf32, int kEpi>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    const int stage_bytes = (kTileM + BN) * p.row_bytes;
+    size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024;
+    const size_t epi = static_cast<size_t>(kTileM) * (BN * 2 + 16) + 1024;
+    if (kEpi == EPI_RAW_STATS && smem < epi) smem = epi;
+    auto kern = tc_gemm_kernel<BN, kTf32, kEpi>;
+    static bool configured = false;
+    if (!configured) {
+        BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    dim3 grid((p.M + kTileM - 1) / kTileM, (p.N + BN - 1) / BN);
+    kern<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, p);
+    BPB_LAUNCH_CHECK("tc_gemm_kernel");
+    return 0;
+}
+
+static int pick_stages(int bn, int row_bytes, int k_iters) {
+    const int stage_bytes = (kTileM + bn) * row_bytes;
+    int s = (96 * 1024) / stage_bytes;
+    if (s > 8) s = 8;
+    if (s > k_iters) s = k_iters;
+    if (s < 2) s = 2;
+    return s;
+}
+
+static int pick_bn(int m_tiles, int cout, int bn_hint) {
+    if (bn_hint > 0) return bn_hint;
+    int bn = cout >= 128 ? 128 : (cout >= 64 ? 64 : 32);
+    // keep at least ~2 waves of CTAs on 148 SMs when the layer is small
+    while (bn > 32 && m_tiles * ((cout + bn - 1) / bn) < 296) bn >>= 1;
+    return bn;
+}
+
+// NHWC bf16 convolution (ksize 1 or 3, stride 1 or 2, pad = ksize/2), raw bf16 output + per-tile BN partials.
+int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
+                 int ksize, int stride, int bn_hint, cudaStream_t stream) {
+    const int pad = ksize / 2;
+    const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (wd + 2 * pad - ksize) / stride + 1;
+    BPB_CHECK(cin % 32 == 0 && cout % 32 == 0, "conv_bf16_tc: channels must be multiples of 32 (cin=%d cout=%d)", cin,
+              cout);
+    BPB_CHECK(wo <= 128 && 128 % wo == 0, "conv_bf16_tc: output width %d must divide 128", wo);
+    const int bh = (128 / wo) < ho ? (128 / wo) : ho;
+    BPB_CHECK(ho % bh == 0, "conv_bf16_tc: output height %d not a multiple of tile rows %d", ho, bh);
+    const int bnimg = 128 / (wo * bh);
+    BPB_CHECK(bnimg * wo * bh == 128, "conv_bf16_tc: tile does not cover 128 pixels (ho=%d wo=%d)", ho, wo);
+    const int kc = cin >= 64 ? 64 : 32;
+    BPB_CHECK(cin % kc == 0, "conv_bf16_tc: cin %d not a multiple of %d", cin, kc);
+
+    GemmParams p{};
+    p.M = n * ho * wo;
+    p.N = cout;
+    p.kchunks = cin / kc;
+    p.k_iters = ksize * ksize * p.kchunks;
+    p.kc = kc;
+    p.cin = cin;
+    p.row_bytes = kc * 2;
+    p.mode = 0;
+    p.ksize = ksize; p.stride = stride; p.pad = pad; p.Ho = ho; p.Wo = wo;
+    p.ldo = cout;
+    p.out = y;
+    p.stats = stats;
+    p.bias = nullptr;
+    const int m_tiles = (p.M + kTileM - 1) / kTileM;
+    const int bn = pick_bn(m_tiles, cout, bn_hint);
+    p.stages = pick_stages(bn, p.row_bytes, p.k_iters);
+
+    const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+        uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)wd * cin * 2, (uint64_t)h * wd * cin * 2};
+        uint32_t box[4] = {(uint32_t)kc, (uint32_t)(wo * stride), (uint32_t)(bh * stride), (uint32_t)bnimg};
+        uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        if (make_tensor_map(&tmA, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box, es, sw)) return 4;
+    }
+    {
+        const uint64_t ktot = (uint64_t)ksize * ksize * cin;
+        uint64_t dims[2] = {ktot, (uint64_t)cout};
+        uint64_t strides[1] = {ktot * 2};
+        uint32_t box[2] = {(uint32_t)kc, (uint32_t)bn};
+        uint32_t es[2] = {1, 1};
+        if (make_tensor_map(&tmB, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, es, sw)) return 4;
+    }
+    switch (bn) {
+        case 32: return launch<32, false, EPI_RAW_STATS>(tmA, tmB, p, stream);
+        case 64: return launch<64, false, EPI_RAW_STATS>(tmA, tmB, p, stream);
+        case 128: return launch<128, false, EPI_RAW_STATS>(tmA, tmB, p, stream);
+        default: BPB_CHECK(false, "conv_bf16_tc: unsupported BN %d", bn);
+    }
+    return 0;
+}
+
+// out[M, N] (fp32, leading dimension ldo) = A[M, K] * W[N, K]^T + bias ; fp32 operands consumed as tf32.
+// a_mode 0: A row-major with leading dimension lda.  a_mode 1: A is the part-major tensor [a_parts, M, K/a_parts]
+// read as the concatenation over parts (bpbreid.py:212 concat_parts_embeddings) without materialising it.
+int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bias, float* out, int m, int n, int k,
+                   int ldo, int a_mode, int a_parts, cudaStream_t stream) {
+    BPB_CHECK(k % 32 == 0, "linear_tf32_tc: K=%d must be a multiple of 32", k);
+    BPB_CHECK(ldo % 4 == 0 && ldo >= n, "linear_tf32_tc: ldo=%d must be >= N and a multiple of 4", ldo);
+    GemmParams p{};
+    p.M = m; p.N = n;
+    p.kc = 32; p.kchunks = k / 32; p.k_iters = p.kchunks; p.cin = k;
+    p.row_bytes = 128;
+    p.mode = a_mode == 0 ? 1 : 2; p.ksize = 1; p.stride = 1; p.pad = 0; p.Ho = 0; p.Wo = 0;
+    p.dchunks = 1;
+    p.ldo = ldo; p.out = out; p.stats = nullptr; p.bias = bias;
+    const int m_tiles = (m + kTileM - 1) / kTileM;
+    int bn = n >= 128 ? 128 : (n >= 64 ? 64 : 32);
+    while (bn > 32 && m_tiles * ((n + bn - 1) / bn) < 148) bn >>= 1;
+    p.stages = pick_stages(bn, 128, p.k_iters);
+    CUtensorMap tmA, tmB;
+    if (a_mode == 0) {
+        BPB_CHECK(lda % 4 == 0 && lda >= k, "linear_tf32_tc: lda=%lld invalid", (long long)lda);
+        uint64_t dims[2] = {(uint64_t)k, (uint64_t)m};
+        uint64_t strides[1] = {(uint64_t)lda * 4};
+        uint32_t box[2] = {32, 128};
+        uint32_t es[2] = {1, 1};
+        if (make_tensor_map(&tmA, a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, es,
+                            CU_TENSOR_MAP_SWIZZLE_128B)) return 4;
+    } else {
+        BPB_CHECK(a_parts > 0 && k % a_parts == 0 && (k / a_parts) % 32 == 0, "linear_tf32_tc: bad part split");
+        const int dd = k / a_parts;
+        p.dchunks = dd / 32;
+        uint64_t dims[3] = {(uint64_t)dd, (uint64_t)m, (uint64_t)a_parts};
+        uint64_t strides[2] = {(uint64_t)dd * 4, (uint64_t)m * dd * 4};
+        uint32_t box[3] = {32, 128, 1};
+        uint32_t es[3] = {1, 1, 1};
+        if (make_tensor_map(&tmA, a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dims, strides, box, es,
+                            CU_TENSOR_MAP_SWIZZLE_128B)) return 4;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)k, (uint64_t)n};
+        uint64_t strides[1] = {(uint64_t)k * 4};
+        uint32_t box[2] = {32, (uint32_t)bn};
+        uint32_t es[2] = {1, 1};
+        if (make_tensor_map(&tmB, w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, es,
+                            CU_TENSOR_MAP_SWIZZLE_128B)) return 4;
+    }
+    switch (bn) {
+        case 32: return launch<32, true, EPI_F32_BIAS>(tmA, tmB, p, stream);
+        case 64: return launch<64, true, EPI_F32_BIAS>(tmA, tmB, p, stream);
+        case 128: return launch<128, true, EPI_F32_BIAS>(tmA, tmB, p, stream);
+    }
+    return 0;
+}
+
+int conv_num_mtiles(int n, int ho, int wo) { return (n * ho * wo + kTileM - 1) / kTileM; }
+
+}  // namespace bpb

@@ -1,0 +1,142 @@
+/* bpbreid_sm100.h -- C ABI of libbpbreid_sm100.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for the BPBReID hot path.  The reference is pure Python: its "FFI" for
+ * this path is the set of tensor-level call sites listed beside each entry point below, so every function
+ * takes raw DEVICE pointers + explicit shapes + a cudaStream_t (passed as void*), never a torch type.
+ *
+ * Conventions
+ *   - the caller owns every buffer (torch tensors in practice, so the caching allocator / CUDA graphs work);
+ *   - work is enqueued on `stream`; nothing synchronises; functions are re-entrant;
+ *   - return value 0 = ok, non-zero = error, message via bpb_last_error() (thread-local);
+ *   - activations are NHWC bf16 ("bf16*" below = uint16_t storage), statistics / heads / losses are fp32;
+ *   - visibility vectors are uint8 (torch.bool storage) when vis_mode == 1, float when vis_mode == 2.
+ */
+#ifndef BPBREID_SM100_H_
+#define BPBREID_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* bpb_last_error(void);
+int bpb_abi_version(void);
+
+/* ---- backbone: replaces nn.Conv2d / nn.BatchNorm2d / ReLU / residual call sites --------------------------- */
+
+/* NHWC bf16 convolution on the tcgen05 tensor cores, ksize in {1,3}, stride in {1,2}, pad = ksize/2, no bias.
+ * Writes the raw (pre-BN) output as bf16 [N*Ho*Wo, cout] and per-128-pixel-tile column sums / sums of squares
+ * `stats` [m_tiles, 2, cout] (m_tiles = bpb_conv_num_mtiles).  w is OHWI bf16 [cout, ksize*ksize*cin].
+ * Replaces: torchreid/models/hrnet.py:60-64,80-96,116-137,222-257,459-483; torchreid/models/resnet.py:43-63,128-154. */
+int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
+                  int ksize, int stride, int bn_hint, void* stream);
+int bpb_conv_num_mtiles(int n, int ho, int wo);
+/* SIMT reference convolution, same operands (validation / shapes the tensor-core tiler rejects). */
+int bpb_conv_ref_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize,
+                      int stride, void* stream);
+/* Stem: NCHW fp32 image (3 ch) -> NHWC bf16 raw output; w is the PyTorch [cout,3,k,k] fp32 weight.
+ * Replaces hrnet.py:533 (3x3 s2) and resnet.py:199-201 / resnet_fastreid.py:246 (7x7 s2). */
+int bpb_stem_conv(const float* img, const float* w, void* y, int n, int h, int wd, int cout, int ksize, int stride,
+                  void* stream);
+/* Column statistics of a bf16 matrix [m, c] -> partials [bpb_colstats_tiles(m), 2, c]. */
+int bpb_colstats_bf16(const void* x, float* partials, int m, int c, void* stream);
+int bpb_colstats_tiles(int m);
+/* partials -> BN scale/shift (train-mode batch statistics, biased variance; running stats updated with momentum and
+ * the unbiased variance exactly like nn.BatchNorm2d; pass NULL to skip).  Parameters cover channels [c_lo, c).
+ * Replaces the nn.BatchNorm2d call sites of hrnet.py:73,77,106-111 etc. in training mode. */
+int bpb_bn_finalize(const float* partials, int tiles, int c, int c_lo, int64_t count, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    float* scale, float* shift, void* stream);
+/* eval mode: scale/shift from the running statistics. */
+int bpb_bn_eval_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                     float eps, int c, float* scale, float* shift, void* stream);
+/* y = act(x*scale + shift [+ res | + res*res_scale + res_shift]) on bf16 [m, c]  (hrnet.py:84-96,123-137). */
+int bpb_bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* res_scale,
+                 const float* res_shift, void* y, int64_t m, int c, int relu, void* stream);
+/* Cross-resolution fuse sum (hrnet.py:269-277): y = relu(sum_j up_nearest_{2^sh_j}(src_j*scale_j+shift_j)). */
+int bpb_fuse_sum(const void* const* srcs, const float* const* scales, const float* const* shifts,
+                 const int* shifts_log2, int nsrc, void* y, int n, int h, int wd, int c, int relu, void* stream);
+/* Bilinear(align_corners=True) upsample + channel concat of the branch maps (hrnet.py:568-573). */
+int bpb_upsample_concat(const void* const* srcs, const int* chans, const int* hs, const int* ws, int nsrc, void* y,
+                        int n, int h, int wd, void* stream);
+/* 3x3 stride-2 max pool (resnet.py:216 pad 1; resnet_fastreid.py:251 pad 0 + ceil_mode). */
+int bpb_maxpool3x3s2(const void* x, void* y, int n, int h, int wd, int c, int pad, int ceil_mode, void* stream);
+/* IBN (resnet_fastreid.py:108-122): per-image statistics of channels [c_lo,c_hi) and the fused IN|BN apply. */
+int bpb_instnorm_stats(const void* x, float* mean_rstd, int n, int hw, int c, int c_lo, int c_hi, float eps,
+                       void* stream);
+int bpb_ibn_apply(const void* x, const float* in_mean_rstd, const float* in_gamma, const float* in_beta,
+                  const float* bn_scale, const float* bn_shift, void* y, int n, int hw, int c, int half, int relu,
+                  void* stream);
+
+/* ---- head: replaces torchreid/models/bpbreid.py:147-219 -------------------------------------------------- */
+
+/* Fold BN2d into the 1x1 pixel classifier (bpbreid.py:383-385). */
+int bpb_pixel_fold(const float* w, const float* b, const float* scale, const float* shift, int kp1, int c, float* wf,
+                   float* bf, void* stream);
+/* Pixel classifier + softmax + masks + visibility (bpbreid.py:147-148,157-192).  feats bf16 [n, hw, c].
+ * logits/probs fp32 [n, K+1, hw]; fg_mask [n, hw]; vis_bits[n] bit k set iff class k is the argmax somewhere;
+ * vis_cont [n, K+1] = amax of the probabilities. */
+int bpb_pixel_classify(const void* feats, const float* wf, const float* bf, int n, int hw, int c, int kp1,
+                       float* logits_nchw, float* probs, float* fg_mask, int* vis_bits, float* vis_cont,
+                       void* stream);
+/* Global / foreground / background / K part pooling in one pass (bpbreid.py:195-202,458-503).
+ * pooled fp32 [K+3, n, c] with rows {0: global, 1: fg, 2: bg, 3..: parts}. */
+int bpb_part_pool(const void* feats, const float* probs, const float* fg_mask, int n, int hw, int c, int kp1,
+                  float* pooled, void* stream);
+/* out[m, n] = A[m, k] W[n, k]^T + bias on tcgen05 (tf32) -- nn.Linear of bpbreid.py:329-334,409.
+ * a_mode 1: A is [a_parts, m, k/a_parts] read as the concat over parts (bpbreid.py:212). */
+int bpb_linear_tf32(const float* a, int64_t lda, const float* w, const float* bias, float* out, int m, int n, int k,
+                    int ldo, int a_mode, int a_parts, void* stream);
+/* nn.BatchNorm1d (+ReLU) on fp32 [m, c] (bpbreid.py:335-336,413). */
+int bpb_bn1d(const float* x, const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+             float* running_var, float* y, int m, int c, int relu, int training, void* stream);
+
+/* Visibility scores (bpbreid.py:182-192): out_b / out_f [n, K+2] = {background, part_1..K, foreground}. */
+int bpb_vis_unpack(const int* vis_bits, const float* vis_cont, int n, int kp1, uint8_t* out_b, float* out_f,
+                   void* stream);
+
+/* ---- GiLt loss: replaces torchreid/losses/{part_averaged_triplet_loss,cross_entropy_loss,
+ *      body_part_attention_loss}.py ------------------------------------------------------------------------ */
+
+/* emb [K, n, d] fp32 (part-major), labels int64 [n], vis [n, K] (uint8 / float) or NULL.
+ * Outputs: dist [n, n], hardest positive / negative value + index per anchor, out4 = {loss, trivial_ratio,
+ * valid_ratio, n_valid} (loss = NaN when n_valid == 0: the caller warns and returns None like
+ * part_averaged_triplet_loss.py:161-163).  margin <= 0 selects the soft-margin variant. */
+int bpb_triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
+                    float margin, float* dist_nn, float* hp, float* hn, int* hp_idx, int* hn_idx, float* out4,
+                    void* stream);
+/* Label-smoothed CE (cross_entropy_loss.py:34-56); scratch has 2n floats; out2 = {loss, top-1 accuracy}. */
+int bpb_ce_ls_fwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c,
+                  float eps, float* scratch, float* out2, void* stream);
+/* Body part attention loss (part_based_engine.py:118-124 + body_part_attention_loss.py:31-52);
+ * partial has 512 floats; out2 = {loss, pixel accuracy}. */
+int bpb_pixel_ce_fwd(const float* logits_nchw, const float* target_masks, int n, int kp1, int hf, int wf, int hm,
+                     int wm, float label_smoothing, float* partial, float* out2, void* stream);
+
+/* out[0] = sum_i weights[i] * terms[i][0]  (GiLt_loss.py:92; `terms` is a host array of device pointers). */
+int bpb_weighted_sum(const float* const* terms, const float* weights, int n, float* out, void* stream);
+
+/* ---- evaluation: replaces torchreid/metrics/distance.py:87-247 and torchreid/metrics/rank.py:97-159 /
+ *      torchreid/metrics/rank_cylib/rank_cy.pyx:154-249 ----------------------------------------------------- */
+
+/* qf [nq, p, d], gf [ng, p, d] fp32.  metric 0 euclidean / 1 cosine; strat 0 mean / 1 max; impl 0 tcgen05 (tf32),
+ * 1 SIMT fp32.  dist [nq, ng]; part_dist [p, nq, ng] or NULL; scratch >= bpb_part_distance_scratch_floats(). */
+int bpb_part_distance(const float* qf, const float* gf, const void* qv, const void* gv, int vis_mode, int nq, int ng,
+                      int p, int d, int metric, int strat, int impl, float* dist, float* part_dist, float* scratch,
+                      void* stream);
+int64_t bpb_part_distance_scratch_floats(int nq, int ng, int p);
+/* market1501 CMC/mAP.  Per-query outputs ap64/ap32/first_rank [nq]; cmc [max_rank]; map_out (fp64 accumulation,
+ * rank.py semantics), map32_out (fp32 accumulation, rank_cy.pyx semantics); num_valid; overflow_flag set when a
+ * query has more matches than the kernel's list can hold. */
+int bpb_rank_market1501(const float* dist, const int64_t* q_pids, const int64_t* g_pids, const int64_t* q_camids,
+                        const int64_t* g_camids, int nq, int ng, int max_rank, double* ap64, float* ap32,
+                        int* first_rank, float* cmc, double* map_out, int64_t* num_valid, float* map32_out,
+                        int* overflow_flag, void* stream);
+/* Stable ascending argsort of every row (== np.argsort(kind='stable')); ng <= 16384. */
+int bpb_argsort_rows(const float* dist, int nq, int ng, int32_t* indices, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPBREID_SM100_H_ */
