@@ -134,7 +134,11 @@ int pixel_classify(const void* feats, const float* wf, const float* bf, int n, i
 #define BPB_PC_CASE(K)                                                                                              \
     case K: {                                                                                                       \
         auto kern = pixel_classify_kernel<K>;                                                                       \
-        BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));              \
+        static bool configured = false;                                                                             \
+        if (!configured) {                                                                                          \
+            BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));          \
+            configured = true;                                                                                      \
+        }                                                                                                           \
         kern<<<blocks, 256, smem, stream>>>(reinterpret_cast<const uint4*>(feats), wf, bf, n, hw, c, logits_nchw,   \
                                             probs, fg_mask, vis_bits, vis_cont);                                    \
         break;                                                                                                      \
@@ -246,7 +250,11 @@ int part_pool(const void* feats, const float* probs, const float* fg_mask, int n
 #define BPB_PP_CASE(JJ)                                                                                         \
     case JJ: {                                                                                                  \
         auto kern = part_pool_kernel<JJ>;                                                                       \
-        BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));          \
+        static bool configured = false;                                                                         \
+        if (!configured) {                                                                                      \
+            BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));      \
+            configured = true;                                                                                  \
+        }                                                                                                       \
         kern<<<grid, 128, smem, stream>>>(reinterpret_cast<const uint4*>(feats), probs, fg_mask, n, hw, c, pooled); \
         break;                                                                                                  \
     }

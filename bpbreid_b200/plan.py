@@ -1,0 +1,515 @@
+"""Forward-pass planner: turns a BPBreID parameter tree + an input shape into a flat list of C-ABI launches
+(libbpbreid_sm100.so) over statically allocated device buffers, so that one training / inference step is a
+replayable sequence (eager loop or CUDA graph).  Python only orchestrates: every number is produced by the
+hand-written sm_100a kernels.
+
+Reference call stack replaced: BPBreID.forward (torchreid/models/bpbreid.py:116-259) ->
+HighResolutionNet.forward (torchreid/models/hrnet.py:532-576) / ResNet.featuremaps (torchreid/models/resnet.py:342-352)
+/ fast-reid ResNet.forward (torchreid/models/resnet_fastreid.py:296-345).
+
+Data layout: activations NHWC bf16; conv weights OHWI bf16 (packed once per plan); BN runs in two phases
+(conv epilogue emits per-tile partial sums -> bn_finalize -> scale/shift consumed by the next elementwise pass);
+pooled embeddings are group-major fp32 [K+3, N, C] = {global, foreground, background, part_0..K-1}.
+"""
+from __future__ import annotations
+
+import ctypes
+from contextlib import contextmanager
+
+import torch
+from torch import nn
+
+from . import _lib
+from . import params as P
+
+BN_EPS = 1e-5
+
+
+class Act:
+    """NHWC bf16 activation."""
+    __slots__ = ("t", "n", "h", "w", "c", "buf")
+
+    def __init__(self, t, n, h, w, c, buf=None):
+        self.t, self.n, self.h, self.w, self.c, self.buf = t, n, h, w, c, buf
+
+    @property
+    def m(self):
+        return self.n * self.h * self.w
+
+
+class Lazy:
+    """Raw conv output + the BN scale/shift that still has to be applied to it."""
+    __slots__ = ("raw", "scale", "shift")
+
+    def __init__(self, raw, scale, shift):
+        self.raw, self.scale, self.shift = raw, scale, shift
+
+
+def _tc_tileable(cin, cout, ho, wo):
+    """Shapes the tcgen05 tiler accepts: 128 output pixels = (images) x (rows) x (full output width)."""
+    if cin % 32 or cout % 32 or wo > 128 or 128 % wo:
+        return False
+    bh = min(ho, 128 // wo)
+    if ho % bh:
+        return False
+    return (128 // (wo * bh)) * wo * bh == 128
+
+
+class ForwardPlan:
+    def __init__(self, model, n, h, w, training, device, conv_impl="tc", use_graph=False):
+        self.model = model
+        self.n, self.h, self.w = n, h, w
+        self.training = bool(training)
+        self.device = device
+        self.conv_impl = conv_impl
+        self.ops = []                 # (ctypes fn, args tuple) ; stream appended at run time
+        self.keepalive = []           # ctypes arrays referenced by ops
+        self.persistent = []          # tensors that must outlive the plan build
+        self._free = {}               # pooled activation buffers by byte size
+        self._scopes = [[]]
+        self.launches = 0
+        self.graph = None
+        self.use_graph = use_graph
+        self.lib = _lib.load()
+        self.cfg = model.model_cfg
+        self.K = model.parts_num
+        self.images = torch.zeros(n, 3, h, w, device=device, dtype=torch.float32)
+        self._packed = {}
+        with torch.no_grad():
+            self._build()
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self, shape, dtype=torch.bfloat16):
+        numel = 1
+        for s in shape:
+            numel *= s
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        lst = self._free.get(nbytes)
+        if lst:
+            buf = lst.pop()
+        else:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._scopes[-1].append(buf)
+        return buf.view(dtype).view(*shape), buf
+
+    def _act(self, n, h, w, c):
+        t, buf = self._alloc((n, h, w, c))
+        return Act(t, n, h, w, c, buf)
+
+    def _small(self, shape, dtype=torch.float32, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+        self.persistent.append(t)
+        return t
+
+    @contextmanager
+    def scope(self):
+        """Activations allocated inside are returned to the pool on exit unless kept."""
+        self._scopes.append([])
+        keep = []
+        try:
+            yield keep
+        finally:
+            mine = self._scopes.pop()
+            kept_ids = {id(a.buf) for a in keep}
+            for buf in mine:
+                if id(buf) in kept_ids:
+                    self._scopes[-1].append(buf)
+                else:
+                    self._free.setdefault(buf.numel(), []).append(buf)
+
+    # ------------------------------------------------------------------ op recording
+    def _op(self, name, *args):
+        self.ops.append((getattr(self.lib, name), args, name))
+        self.launches += 1
+
+    def _ptr_array(self, tensors):
+        arr = (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+        self.keepalive.append(arr)
+        return ctypes.cast(arr, ctypes.c_void_p)
+
+    def _int_array(self, vals):
+        arr = (ctypes.c_int * len(vals))(*vals)
+        self.keepalive.append(arr)
+        return ctypes.cast(arr, ctypes.c_void_p)
+
+    def _float_array(self, vals):
+        arr = (ctypes.c_float * len(vals))(*vals)
+        self.keepalive.append(arr)
+        return ctypes.cast(arr, ctypes.c_void_p)
+
+    # ------------------------------------------------------------------ weights
+    def pack_conv(self, conv: nn.Conv2d):
+        key = id(conv)
+        if key not in self._packed:
+            w = conv.weight.detach()
+            self._packed[key] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+        return self._packed[key]
+
+    def refresh_weights(self):
+        """Re-pack the bf16 OHWI copies after the fp32 master weights changed."""
+        for mod in self.model.modules():
+            if isinstance(mod, nn.Conv2d) and id(mod) in self._packed:
+                w = mod.weight.detach()
+                self._packed[id(mod)].copy_(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))
+
+    # ------------------------------------------------------------------ building blocks
+    def _bn_params(self, bn, c_lo=0):
+        return bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum if bn.momentum is not None else 0.1
+
+    def bn_scale_shift(self, stats, tiles, c, count, bn, c_lo=0):
+        """partials -> (scale, shift) for nn.BatchNorm2d `bn` (train: batch stats, eval: running stats)."""
+        scale, shift = self._small((c,)), self._small((c,))
+        g, b, rm, rv, mom = self._bn_params(bn)
+        if self.training:
+            self._op("bpb_bn_finalize", stats.data_ptr(), tiles, c, c_lo, count, g.data_ptr(), b.data_ptr(),
+                     BN_EPS, float(mom), rm.data_ptr(), rv.data_ptr(), scale.data_ptr(), shift.data_ptr())
+        else:
+            assert c_lo == 0
+            self._op("bpb_bn_eval_fold", g.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(), BN_EPS, c,
+                     scale.data_ptr(), shift.data_ptr())
+        return scale, shift
+
+    def conv_raw(self, x: Act, conv: nn.Conv2d, need_stats=True):
+        k, s = conv.kernel_size[0], conv.stride[0]
+        cout = conv.out_channels
+        pad = k // 2
+        ho = (x.h + 2 * pad - k) // s + 1
+        wo = (x.w + 2 * pad - k) // s + 1
+        y = self._act(x.n, ho, wo, cout)
+        wp = self.pack_conv(conv)
+        tc_ok = self.conv_impl == "tc" and _tc_tileable(x.c, cout, ho, wo)
+        stats, tiles = None, 0
+        if tc_ok:
+            tiles = _lib.query("bpb_conv_num_mtiles", x.n, ho, wo)
+            if need_stats and self.training:
+                stats = self._small((tiles, 2, cout))
+            self._op("bpb_conv_bf16", x.t.data_ptr(), wp.data_ptr(), y.t.data_ptr(), _lib.ptr(stats), x.n, x.h, x.w,
+                     x.c, cout, k, s, 0)
+        else:
+            self._op("bpb_conv_ref_bf16", x.t.data_ptr(), wp.data_ptr(), y.t.data_ptr(), x.n, x.h, x.w, x.c, cout, k, s)
+            if need_stats and self.training:
+                stats, tiles = self.colstats(y)
+        return y, stats, tiles
+
+    def colstats(self, y: Act):
+        tiles = _lib.query("bpb_colstats_tiles", y.m)
+        stats = self._small((tiles, 2, y.c))
+        self._op("bpb_colstats_bf16", y.t.data_ptr(), stats.data_ptr(), y.m, y.c)
+        return stats, tiles
+
+    def conv_bn(self, x: Act, conv, bn) -> Lazy:
+        y, stats, tiles = self.conv_raw(x, conv)
+        scale, shift = self.bn_scale_shift(stats, tiles, y.c, y.m, bn)
+        return Lazy(y, scale, shift)
+
+    def apply(self, lz: Lazy, relu, res=None) -> Act:
+        """y = act(bn(raw) + res) ; res may be an Act (identity skip) or a Lazy (projection skip)."""
+        r = lz.raw
+        y = self._act(r.n, r.h, r.w, r.c)
+        if res is None:
+            rp, rs, rb = None, None, None
+        elif isinstance(res, Lazy):
+            rp, rs, rb = res.raw.t.data_ptr(), res.scale.data_ptr(), res.shift.data_ptr()
+        else:
+            rp, rs, rb = res.t.data_ptr(), None, None
+        self._op("bpb_bn_apply", r.t.data_ptr(), lz.scale.data_ptr(), lz.shift.data_ptr(), rp, rs, rb, y.t.data_ptr(),
+                 r.m, r.c, 1 if relu else 0)
+        return y
+
+    def basic_block(self, x: Act, blk) -> Act:
+        with self.scope() as keep:
+            a = self.apply(self.conv_bn(x, blk.conv1, blk.bn1), True)
+            y = self.apply(self.conv_bn(a, blk.conv2, blk.bn2), True, res=x)
+            keep.append(y)
+        return y
+
+    def bottleneck(self, x: Act, blk) -> Act:
+        with self.scope() as keep:
+            if isinstance(blk.bn1, P.IBNPair):
+                a = self.ibn_relu(x, blk.conv1, blk.bn1)
+            else:
+                a = self.apply(self.conv_bn(x, blk.conv1, blk.bn1), True)
+            b = self.apply(self.conv_bn(a, blk.conv2, blk.bn2), True)
+            l3 = self.conv_bn(b, blk.conv3, blk.bn3)
+            if blk.downsample is not None:
+                res = self.conv_bn(x, blk.downsample[0], blk.downsample[1])
+            else:
+                res = x
+            y = self.apply(l3, True, res=res)
+            keep.append(y)
+        return y
+
+    def ibn_relu(self, x: Act, conv, ibn) -> Act:
+        """conv -> IBN (InstanceNorm first half | BatchNorm second half) -> ReLU (resnet_fastreid.py:108-122,224-226)."""
+        raw, stats, tiles = self.conv_raw(x, conv)
+        c, half = raw.c, ibn.half
+        bn = ibn.BN
+        scale, shift = self._small((c,)), self._small((c,))
+        if self.training:
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            self._op("bpb_bn_finalize", stats.data_ptr(), tiles, c, half, raw.m, bn.weight.data_ptr(),
+                     bn.bias.data_ptr(), BN_EPS, float(mom), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                     scale.data_ptr(), shift.data_ptr())
+        else:
+            self._op("bpb_bn_eval_fold", bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                     bn.running_var.data_ptr(), BN_EPS, c - half, scale[half:].data_ptr(), shift[half:].data_ptr())
+        mr = self._small((raw.n, half, 2))
+        self._op("bpb_instnorm_stats", raw.t.data_ptr(), mr.data_ptr(), raw.n, raw.h * raw.w, c, 0, half, BN_EPS)
+        y = self._act(raw.n, raw.h, raw.w, c)
+        self._op("bpb_ibn_apply", raw.t.data_ptr(), mr.data_ptr(), ibn.IN.weight.data_ptr(), ibn.IN.bias.data_ptr(),
+                 scale.data_ptr(), shift.data_ptr(), y.t.data_ptr(), raw.n, raw.h * raw.w, c, half, 1)
+        return y
+
+    def fuse(self, terms, out_like: Act, relu=True) -> Act:
+        """terms: list of (Act | Lazy, log2 upsample factor)"""
+        y = self._act(out_like.n, out_like.h, out_like.w, out_like.c)
+        srcs, scs, shs, ups = [], [], [], []
+        for t, up in terms:
+            if isinstance(t, Lazy):
+                srcs.append(t.raw.t); scs.append(t.scale); shs.append(t.shift)
+            else:
+                srcs.append(t.t); scs.append(None); shs.append(None)
+            ups.append(up)
+        self._op("bpb_fuse_sum", self._ptr_array(srcs), self._ptr_array(scs), self._ptr_array(shs),
+                 self._int_array(ups), len(terms), y.t.data_ptr(), y.n, y.h, y.w, y.c, 1 if relu else 0)
+        return y
+
+    def stem(self, conv, bn, ksize, stride) -> Act:
+        n, h, w = self.n, self.h, self.w
+        pad = ksize // 2
+        ho, wo = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
+        raw = self._act(n, ho, wo, conv.out_channels)
+        wt = conv.weight.detach()
+        self._op("bpb_stem_conv", self.images.data_ptr(), wt.data_ptr(), raw.t.data_ptr(), n, h, w, conv.out_channels,
+                 ksize, stride)
+        stats, tiles = (self.colstats(raw) if self.training else (None, 0))
+        scale, shift = self.bn_scale_shift(stats, tiles, raw.c, raw.m, bn)
+        return self.apply(Lazy(raw, scale, shift), True)
+
+    # ------------------------------------------------------------------ backbones
+    def hr_module(self, xs, mod):
+        nb = len(xs)
+        with self.scope() as keep:
+            ys = []
+            for b in range(nb):
+                t = xs[b]
+                for blk in mod.branches[b]:
+                    t = self.basic_block(t, blk)
+                ys.append(t)
+            outs = []
+            for i in range(nb):
+                terms = []
+                for j in range(nb):
+                    if j == i:
+                        terms.append((ys[j], 0))
+                    elif j > i:
+                        f = mod.fuse_layers[i][j]
+                        terms.append((self.conv_bn(ys[j], f[0], f[1]), j - i))
+                    else:
+                        t = ys[j]
+                        chain = mod.fuse_layers[i][j]
+                        for k, st in enumerate(chain):
+                            lz = self.conv_bn(t, st[0], st[1])
+                            if k == len(chain) - 1:
+                                terms.append((lz, 0))
+                            else:
+                                t = self.apply(lz, True)
+                outs.append(self.fuse(terms, ys[i]))
+            keep.extend(outs)
+        return outs
+
+    def build_hrnet(self, bb):
+        with self.scope() as keep:
+            x = self.stem(bb.conv1, bb.bn1, 3, 2)
+            x = self.apply(self.conv_bn(x, bb.conv2, bb.bn2), True)
+            for blk in bb.layer1:
+                x = self.bottleneck(x, blk)
+            t = bb.transition1
+            xs = [self.apply(self.conv_bn(x, t[0][0], t[0][1]), True),
+                  self.apply(self.conv_bn(x, t[1][0][0], t[1][0][1]), True)]
+            for mod in bb.stage2:
+                xs = self.hr_module(xs, mod)
+            t = bb.transition2[2][0]
+            xs = xs + [self.apply(self.conv_bn(xs[-1], t[0], t[1]), True)]
+            for mod in bb.stage3:
+                xs = self.hr_module(xs, mod)
+            t = bb.transition3[3][0]
+            xs = xs + [self.apply(self.conv_bn(xs[-1], t[0], t[1]), True)]
+            for mod in bb.stage4:
+                xs = self.hr_module(xs, mod)
+            br = [self.bottleneck(xs[i], bb.incre_modules[i][0]) for i in range(4)]
+            feats = self._act(self.n, br[0].h, br[0].w, sum(b.c for b in br))
+            self._op("bpb_upsample_concat", self._ptr_array([b.t for b in br]), self._int_array([b.c for b in br]),
+                     self._int_array([b.h for b in br]), self._int_array([b.w for b in br]), 4, feats.t.data_ptr(),
+                     self.n, feats.h, feats.w)
+            keep.append(feats)
+        return feats
+
+    def build_resnet(self, bb):
+        with self.scope() as keep:
+            x = self.stem(bb.conv1, bb.bn1, 7, 2)
+            pad, ceil = (0, 1) if bb.fastreid else (1, 0)
+            num_h, num_w = x.h + 2 * pad - 3, x.w + 2 * pad - 3
+            ho = ((num_h + 1) // 2 if ceil else num_h // 2) + 1
+            wo = ((num_w + 1) // 2 if ceil else num_w // 2) + 1
+            if ceil and (ho - 1) * 2 >= x.h + pad:
+                ho -= 1
+            if ceil and (wo - 1) * 2 >= x.w + pad:
+                wo -= 1
+            y = self._act(x.n, ho, wo, x.c)
+            self._op("bpb_maxpool3x3s2", x.t.data_ptr(), y.t.data_ptr(), x.n, x.h, x.w, x.c, pad, ceil)
+            x = y
+            for li in range(1, 5):
+                for blk in getattr(bb, f"layer{li}"):
+                    x = self.bottleneck(x, blk)
+            keep.append(x)
+        return x
+
+    # ------------------------------------------------------------------ head
+    def build_head(self, feats: Act):
+        m, K, n = self.model, self.K, self.n
+        kp1, J = K + 1, K + 3
+        hw, c = feats.h * feats.w, feats.c
+        D = m.dim_reduce_output
+        ncls = m.num_classes
+        ld = (ncls + 3) // 4 * 4
+        self.feats = feats
+        pc = m.pixel_classifier
+        # pixel classifier: BN2d statistics over the map, folded into the 1x1 conv
+        if self.training:
+            stats, tiles = self.colstats(Act(feats.t, n, feats.h, feats.w, c))
+        else:
+            stats, tiles = None, 0
+        scale, shift = self.bn_scale_shift(stats, tiles, c, n * hw, pc.bn)
+        wf, bf = self._small((kp1, c)), self._small((kp1,))
+        self._op("bpb_pixel_fold", pc.classifier.weight.data_ptr(), pc.classifier.bias.data_ptr(), scale.data_ptr(),
+                 shift.data_ptr(), kp1, c, wf.data_ptr(), bf.data_ptr())
+        self.logits = self._small((n, kp1, feats.h, feats.w))
+        self.probs = self._small((n, kp1, feats.h, feats.w))
+        self.fg_mask = self._small((n, feats.h, feats.w))
+        self.vis_bits = self._small((n,), torch.int32)
+        self.vis_cont = self._small((n, kp1))
+        self._op("bpb_pixel_classify", feats.t.data_ptr(), wf.data_ptr(), bf.data_ptr(), n, hw, c, kp1,
+                 self.logits.data_ptr(), self.probs.data_ptr(), self.fg_mask.data_ptr(), self.vis_bits.data_ptr(),
+                 self.vis_cont.data_ptr())
+        self.vis_b = self._small((n, kp1 + 1), torch.uint8)
+        self.vis_f = self._small((n, kp1 + 1))
+        self._op("bpb_vis_unpack", self.vis_bits.data_ptr(), self.vis_cont.data_ptr(), n, kp1, self.vis_b.data_ptr(),
+                 self.vis_f.data_ptr())
+        self.pooled = self._small((J, n, c))
+        self._op("bpb_part_pool", feats.t.data_ptr(), self.probs.data_ptr(), self.fg_mask.data_ptr(), n, hw, c, kp1,
+                 self.pooled.data_ptr())
+        # dim reduce: Linear(C->D) + BN1d + ReLU for {global, fg, bg, parts (K*N rows jointly)}
+        lin = self._small((J * n, D))
+        self.emb = self._small((J * n, D))
+        groups = [(m.global_after_pooling_dim_reduce, 0, n), (m.foreground_after_pooling_dim_reduce, n, n),
+                  (m.background_after_pooling_dim_reduce, 2 * n, n), (m.parts_after_pooling_dim_reduce, 3 * n, K * n)]
+        pooled2d = self.pooled.view(J * n, c)
+        for dr, r0, rows in groups:
+            fc, bn = dr.layers[0], dr.layers[1]
+            self._op("bpb_linear_tf32", pooled2d[r0:].data_ptr(), c, fc.weight.data_ptr(), fc.bias.data_ptr(),
+                     lin[r0:].data_ptr(), rows, D, c, D, 0, 0)
+            self._bn1d(lin[r0:], bn, self.emb[r0:], rows, D, relu=True)
+        # BN classifiers
+        self.bn_emb = self._small((J * n, D))
+        self.bn_conct = self._small((K * n, D))
+        self.scores = self._small((J * n, ld))
+        self.scores_conct = self._small((n, ld))
+        heads = [(m.global_identity_classifier, 0), (m.foreground_identity_classifier, n),
+                 (m.background_identity_classifier, 2 * n)]
+        if m.shared_parts_id_classifier:
+            heads_parts = [(m.parts_identity_classifier, 3 * n, K * n)]
+        else:
+            heads_parts = [(m.parts_identity_classifier[k], (3 + k) * n, n) for k in range(K)]
+        for cl, r0 in heads:
+            self._bn_classifier(cl, self.emb[r0:], self.bn_emb[r0:], self.scores[r0:], n, D, ncls, ld)
+        for cl, r0, rows in heads_parts:
+            self._bn_classifier(cl, self.emb[r0:], self.bn_emb[r0:], self.scores[r0:], rows, D, ncls, ld)
+        # concat-parts classifier: BN1d over [N, K*D] == per-part BN1d with the matching parameter slice
+        cc = m.concat_parts_identity_classifier
+        for k in range(K):
+            sl = slice(k * D, (k + 1) * D)
+            self._op("bpb_bn1d", self.emb[(3 + k) * n:].data_ptr(), cc.bn.weight[sl].data_ptr(),
+                     cc.bn.bias[sl].data_ptr(), BN_EPS, 0.1, cc.bn.running_mean[sl].data_ptr(),
+                     cc.bn.running_var[sl].data_ptr(), self.bn_conct[k * n:].data_ptr(), n, D, 0,
+                     1 if self.training else 0)
+        self._op("bpb_linear_tf32", self.bn_conct.data_ptr(), D, cc.classifier.weight.data_ptr(), None,
+                 self.scores_conct.data_ptr(), n, ncls, K * D, ld, 1, K)
+        self.ncls, self.ld, self.D = ncls, ld, D
+
+    def _bn1d(self, x, bn, y, rows, c, relu):
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        self._op("bpb_bn1d", x.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS, float(mom),
+                 bn.running_mean.data_ptr(), bn.running_var.data_ptr(), y.data_ptr(), rows, c, 1 if relu else 0,
+                 1 if self.training else 0)
+
+    def _bn_classifier(self, cl, x, bn_out, scores, rows, D, ncls, ld):
+        self._bn1d(x, cl.bn, bn_out, rows, D, relu=False)
+        self._op("bpb_linear_tf32", bn_out.data_ptr(), D, cl.classifier.weight.data_ptr(), None, scores.data_ptr(),
+                 rows, ncls, D, ld, 0, 0)
+
+    # ------------------------------------------------------------------ build / run
+    def _build(self):
+        bb = self.model.backbone_appearance_feature_extractor
+        if not self.cfg.learnable_attention_enabled:
+            raise NotImplementedError("external-mask attention (learnable_attention_enabled=False) is not built yet")
+        if self.cfg.dim_reduce != "after_pooling" or self.cfg.pooling != "gwap" or self.cfg.normalization != "identity":
+            raise NotImplementedError("only the shipped configuration (gwap / identity / after_pooling) is built")
+        if isinstance(bb, P.HRNet32Params):
+            feats = self.build_hrnet(bb)
+        elif isinstance(bb, P.ResNet50Params):
+            feats = self.build_resnet(bb)
+        else:
+            raise KeyError(f"unknown backbone container {type(bb)}")
+        self.build_head(feats)
+
+    def _launch_all(self):
+        stream = torch.cuda.current_stream().cuda_stream
+        err = self.lib.bpb_last_error
+        for fn, args, name in self.ops:
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise RuntimeError(f"{name} failed (rc={rc}): {err().decode()}")
+
+    def run(self, images):
+        self.images.copy_(images, non_blocking=True)
+        if self.use_graph:
+            if self.graph is None:
+                # warm-up outside capture (first-call attribute setup), then capture
+                self._launch_all()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_all()
+                self.graph = g
+            self.graph.replay()
+        else:
+            self._launch_all()
+
+    # ------------------------------------------------------------------ reference-shaped outputs
+    def outputs(self):
+        """The 6-tuple of BPBreID.forward (bpbreid.py:222-259) as views of the plan's buffers."""
+        n, K, D, ncls = self.n, self.K, self.D, self.ncls
+        e, be, sc = self.emb, self.bn_emb, self.scores
+        parts = e[3 * n:].view(K, n, D).permute(1, 0, 2)
+        bn_parts = be[3 * n:].view(K, n, D).permute(1, 0, 2)
+        binary = (self.training and self.cfg.training_binary_visibility_score) or \
+                 (not self.training and self.cfg.testing_binary_visibility_score)
+        vis = self.vis_b.view(torch.bool) if binary else self.vis_f
+        embeddings = {
+            "globl": e[0:n], "backg": e[2 * n:3 * n], "foreg": e[n:2 * n],
+            "conct": parts.reshape(n, K * D), "parts": parts,
+            "bn_globl": be[0:n], "bn_backg": be[2 * n:3 * n], "bn_foreg": be[n:2 * n],
+            "bn_conct": self.bn_conct.view(K, n, D).permute(1, 0, 2).reshape(n, K * D), "bn_parts": bn_parts,
+        }
+        fg_v = vis[:, K + 1]
+        visibility = {"globl": torch.ones_like(fg_v), "backg": vis[:, 0], "foreg": fg_v, "conct": fg_v,
+                      "parts": vis[:, 1:K + 1]}
+        scores = {"globl": sc[0:n, :ncls], "backg": sc[2 * n:3 * n, :ncls], "foreg": sc[n:2 * n, :ncls],
+                  "conct": self.scores_conct[:, :ncls],
+                  "parts": sc[3 * n:].view(K, n, self.ld).permute(1, 0, 2)[:, :, :ncls]}
+        f = self.feats
+        spatial = f.t.view(n, f.h, f.w, f.c).permute(0, 3, 1, 2)
+        masks = {"globl": torch.ones_like(self.fg_mask), "backg": self.probs[:, 0], "foreg": self.fg_mask,
+                 "conct": self.fg_mask, "parts": self.probs[:, 1:]}
+        return embeddings, visibility, scores, self.logits, spatial, masks

@@ -1,0 +1,159 @@
+"""ORACLE tooling (test infrastructure only): mints the golden vectors under tests/golden/ by running the
+UNMODIFIED reference modules (imported from /root/reference through oracle/ref_loader.py) on seeded inputs.
+
+Run in the build container only (the GPU box has no /root/reference):   python oracle/make_golden.py
+Everything it writes is small (< 1 MB per file); model weights are NOT stored -- they are regenerated from a seed
+with bpbreid_b200.params.seeded_state_dict (deterministic CPU RNG, same torch build on both machines).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from tests.golden_inputs import (distance_case, loss_case, model_case, rank_case, LOSS_CASES, DIST_CASES,  # noqa: E402
+                                 RANK_CASES, MODEL_CASES)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def t2n(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def gen_losses(ref):
+    out = {}
+    for name in LOSS_CASES:
+        c = loss_case(name)
+        g = ref.GiLtLoss(c["weights"], use_visibility_scores=c["use_vis"], triplet_margin=c["margin"],
+                         loss_name="part_averaged_triplet_loss", writer=ref_loader.NoOpWriter())
+        emb = {k: torch.from_numpy(v) for k, v in c["emb"].items()}
+        vis = {k: torch.from_numpy(v) for k, v in c["vis"].items()}
+        ids = {k: torch.from_numpy(v) for k, v in c["ids"].items()}
+        pids = torch.from_numpy(c["pids"])
+        loss, summary = g(emb, vis, ids, pids)
+        out[f"{name}/loss"] = t2n(loss)
+        for key, info in summary.items():
+            for kk, vv in info.items():
+                out[f"{name}/{key}/{kk}"] = t2n(vv).astype(np.float64)
+        # the triplet building blocks on their own
+        tl = ref.losses.PartAveragedTripletLoss(margin=c["margin"], writer=ref_loader.NoOpWriter())
+        pd = tl._part_based_pairwise_distance_matrix(emb["parts"].transpose(1, 0), squared=False)
+        out[f"{name}/part_pairwise"] = t2n(pd)
+    # body part attention loss
+    torch.manual_seed(7)
+    logits = torch.randn(3, 6, 16, 8)
+    masks = torch.softmax(3 * torch.randn(3, 6, 9, 5), 1)
+    tm = torch.nn.functional.interpolate(masks, logits.shape[2:], mode="bilinear", align_corners=True)
+    tgt = tm.argmax(1)
+    bpa = ref.BodyPartAttentionLoss(loss_type="cl", label_smoothing=0.1)
+    l, s = bpa(logits, tgt)
+    out["bpa/logits"], out["bpa/masks"] = t2n(logits), t2n(masks)
+    out["bpa/loss"], out["bpa/acc"] = t2n(l), np.float64(s["pixls"]["a"])
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
+    print("losses.npz", len(out))
+
+
+def gen_distance(ref):
+    out = {}
+    for name in DIST_CASES:
+        c = distance_case(name)
+        qv = None if c["qv"] is None else torch.from_numpy(c["qv"])
+        gv = None if c["gv"] is None else torch.from_numpy(c["gv"])
+        d, pd = ref.distance.compute_distance_matrix_using_bp_features(
+            torch.from_numpy(c["qf"]), torch.from_numpy(c["gf"]), qv, gv, c["strat"], 17, False, c["metric"])
+        out[f"{name}/dist"], out[f"{name}/part_dist"] = t2n(d), t2n(pd)
+    np.savez_compressed(os.path.join(OUT, "distance.npz"), **out)
+    print("distance.npz", len(out))
+
+
+def gen_rank(ref):
+    out = {}
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    try:
+        import rank_cy  # the reference's own Cython module, built by oracle/build.py --ref
+    except ImportError:
+        rank_cy = None
+    for name in RANK_CASES:
+        c = rank_case(name)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = ref.rank.eval_market1501(c["dist"], c["q_pids"], c["g_pids"], c["q_camids"], c["g_camids"], c["max_rank"])
+        out[f"{name}/cmc"], out[f"{name}/mAP"] = np.asarray(r["cmc"]), np.float64(r["mAP"])
+        # same unmodified reference code with numpy's sort pinned to the stable kind (the ranking contract:
+        # the reference's default introsort is free to permute tie groups, SURVEY.md section 7 hard part 5)
+        orig = np.argsort
+        np.argsort = lambda a, axis=-1, kind=None, order=None: orig(a, axis=axis, kind="stable")
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                rs_ = ref.rank.eval_market1501(c["dist"], c["q_pids"], c["g_pids"], c["q_camids"], c["g_camids"],
+                                               c["max_rank"])
+            out[f"{name}/cmc_stable"], out[f"{name}/mAP_stable"] = np.asarray(rs_["cmc"]), np.float64(rs_["mAP"])
+            if rank_cy is not None:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    cmc_s, map_s = rank_cy.evaluate_cy(c["dist"], c["q_pids"], c["g_pids"], c["q_camids"],
+                                                       c["g_camids"], c["max_rank"])
+                out[f"{name}/cy_cmc_stable"], out[f"{name}/cy_mAP_stable"] = np.asarray(cmc_s), np.float64(map_s)
+        finally:
+            np.argsort = orig
+        if rank_cy is not None:
+            with contextlib.redirect_stdout(io.StringIO()):
+                cmc, m_ap = rank_cy.evaluate_cy(c["dist"], c["q_pids"], c["g_pids"], c["q_camids"], c["g_camids"],
+                                                c["max_rank"])
+            out[f"{name}/cy_cmc"], out[f"{name}/cy_mAP"] = np.asarray(cmc), np.float64(m_ap)
+    np.savez_compressed(os.path.join(OUT, "rank.npz"), **out)
+    print("rank.npz", len(out))
+
+
+def gen_models(ref):
+    for name in MODEL_CASES:
+        c = model_case(name)
+        m = ref_loader.build_reference_model(c["backbone"], c["K"], c["num_classes"])
+        missing = m.load_state_dict(c["state_dict"], strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        out = {}
+        for mode in ("train", "eval"):
+            m.train(mode == "train")
+            # fresh copy of running stats each time so that train-mode side effects do not leak into eval
+            m.load_state_dict(c["state_dict"], strict=True)
+            with torch.no_grad():
+                emb, vis, ids, pix, feats, masks = m(torch.from_numpy(c["images"]))
+            for k, v in emb.items():
+                out[f"{mode}/emb/{k}"] = t2n(v)
+            for k, v in vis.items():
+                out[f"{mode}/vis/{k}"] = t2n(v)
+            for k, v in ids.items():
+                out[f"{mode}/ids/{k}"] = t2n(v)
+            out[f"{mode}/pix"] = t2n(pix)
+            out[f"{mode}/feat_mean"] = t2n(feats.mean(dim=(2, 3)))
+            out[f"{mode}/feat_abs_mean"] = t2n(feats.abs().mean())
+            if mode == "train":
+                g = ref.GiLtLoss(None, use_visibility_scores=False, triplet_margin=0.3,
+                                 loss_name="part_averaged_triplet_loss", writer=ref_loader.NoOpWriter())
+                loss, _ = g(emb, vis, ids, torch.from_numpy(c["pids"]))
+                out["train/gilt_loss"] = t2n(loss)
+        np.savez_compressed(os.path.join(OUT, f"model_{name}.npz"), **out)
+        print(f"model_{name}.npz", len(out))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_loader.load()
+    which = sys.argv[1:] or ["losses", "distance", "rank", "models"]
+    if "losses" in which:
+        gen_losses(ref)
+    if "distance" in which:
+        gen_distance(ref)
+    if "rank" in which:
+        gen_rank(ref)
+    if "models" in which:
+        gen_models(ref)

@@ -64,7 +64,8 @@ int oracle_eval_market1501(const float *distmat, const int64_t *q_pids, const in
         /* AP from the unclipped cumsum (rank_cy.pyx:219-225) */
         float num_rel = 0.f, tmp_sum = 0.f;
         for (long g = 0; g < num_g_real; ++g) {
-            tmp_sum += (cmc[g] / (g + 1.f)) * raw_cmc[g];
+            /* Cython: float / (long + 1.) promotes to double; the float accumulator is rounded once per term */
+            tmp_sum = (float)((double)tmp_sum + ((double)cmc[g] / ((double)g + 1.)) * (double)raw_cmc[g]);
             num_rel += raw_cmc[g];
         }
         /* NB: entries beyond num_g_real keep stale values in the reference's reused buffer; with

@@ -1,0 +1,157 @@
+"""Seeded input generators shared by oracle/make_golden.py (which runs the reference on them, in the build
+container) and the parity tests (which run the oracle restatements and the CUDA path on the same inputs).
+Only numpy / torch CPU RNGs: bit-identical on the build container and on the GPU box (same image)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+F32 = np.float32
+GL, FG, CC, PA = "globl", "foreg", "conct", "parts"
+
+DEFAULT_W = {GL: {"id": 1., "tr": 0.}, FG: {"id": 1., "tr": 0.}, CC: {"id": 1., "tr": 0.}, PA: {"id": 0., "tr": 1.}}
+MARKET_W = {GL: {"id": 1., "tr": 0.}, FG: {"id": 1., "tr": 1.}, CC: {"id": 1., "tr": 0.}, PA: {"id": 0., "tr": 1.}}
+
+LOSS_CASES = ["default", "market", "vis_bool", "vis_float", "dups_singletons", "soft_margin"]
+
+
+def loss_case(name, n=32, k=5, d=64, ncls=41):
+    rs = np.random.RandomState({"default": 1, "market": 2, "vis_bool": 3, "vis_float": 4, "dups_singletons": 5,
+                                "soft_margin": 6}[name])
+    pids = (np.arange(n) // 4).astype(np.int64)
+    parts = rs.randn(n, k, d).astype(F32)
+    c = dict(weights=DEFAULT_W, use_vis=False, margin=0.3)
+    if name == "market":
+        c["weights"] = MARKET_W
+    if name == "soft_margin":
+        c["margin"] = 0.0
+    vis_parts = np.ones((n, k), dtype=bool)
+    vis_h = np.ones(n, dtype=bool)
+    if name == "vis_bool":
+        c["use_vis"] = True
+        c["weights"] = MARKET_W
+        vis_parts = rs.rand(n, k) > 0.35
+        vis_parts[3] = False                     # a sample with no visible part at all -> -1 sentinels
+        vis_parts[8, :] = [True, False, False, False, False]
+        vis_parts[9, :] = [False, True, False, False, False]   # 8 and 9 share an id but no visible part
+        vis_h = vis_parts.any(1)
+    if name == "vis_float":
+        c["use_vis"] = True
+        vis_parts = rs.rand(n, k).astype(F32)
+        vis_parts[5] = 0
+        vis_h = vis_parts.max(1)
+    if name == "dups_singletons":
+        parts[1] = parts[0]                      # exact duplicates -> exact-zero distance mask
+        parts[6] = parts[2]                      # duplicate across identities
+        pids[-4:] = [100, 101, 102, 103]         # singleton identities -> anchors without positives
+    emb = {GL: rs.randn(n, d).astype(F32), FG: rs.randn(n, d).astype(F32), PA: parts,
+           CC: parts.reshape(n, k * d).copy()}
+    ids = {GL: rs.randn(n, ncls).astype(F32), FG: rs.randn(n, ncls).astype(F32), CC: rs.randn(n, ncls).astype(F32),
+           PA: rs.randn(n, k, ncls).astype(F32)}
+    vis = {GL: np.ones(n, dtype=vis_h.dtype), FG: vis_h, CC: vis_h, PA: vis_parts}
+    pid_cls = (pids % ncls).astype(np.int64)
+    c.update(emb=emb, ids=ids, vis=vis, pids=pid_cls)
+    return c
+
+
+DIST_CASES = ["novis_mean", "novis_max", "bool_mean", "bool_max", "float_mean", "bool_mean_cosine", "ragged"]
+
+
+def distance_case(name):
+    seed = DIST_CASES.index(name) + 11
+    rs = np.random.RandomState(seed)
+    nq, ng, p, d = (37, 91, 6, 64) if name != "ragged" else (5, 131, 3, 96)
+    qf = rs.randn(nq, p, d).astype(F32)
+    gf = rs.randn(ng, p, d).astype(F32)
+    qf /= np.linalg.norm(qf, axis=-1, keepdims=True)
+    gf /= np.linalg.norm(gf, axis=-1, keepdims=True)
+    gf[7] = qf[3]                                  # exact duplicates -> zero distances / ties
+    gf[8] = qf[3]
+    c = dict(qf=qf, gf=gf, qv=None, gv=None, strat="mean", metric="euclidean")
+    if "max" in name:
+        c["strat"] = "max"
+    if "cosine" in name:
+        c["metric"] = "cosine"
+    if name.startswith("bool") or name == "ragged":
+        qv, gv = rs.rand(nq, p) > 0.3, rs.rand(ng, p) > 0.3
+        qv[1] = False                              # query with nothing visible -> whole row is the sentinel
+        gv[4] = False
+        qv[2] = [True] + [False] * (p - 1)
+        gv[5] = [False] + [True] * (p - 1)         # (2,5): no common visible part
+        c["qv"], c["gv"] = qv, gv
+    if name.startswith("float"):
+        qv, gv = rs.rand(nq, p).astype(F32), rs.rand(ng, p).astype(F32)
+        qv[1] = 0
+        c["qv"], c["gv"] = qv, gv
+    return c
+
+
+RANK_CASES = ["random", "ties", "small_gallery", "some_invalid"]
+
+
+def rank_case(name):
+    rs = np.random.RandomState(RANK_CASES.index(name) + 31)
+    nq, ng, max_rank = 60, 400, 50
+    if name == "small_gallery":
+        nq, ng = 12, 30                           # max_rank > Ng
+    dist = rs.rand(nq, ng).astype(F32)
+    npid = 25
+    q_pids, g_pids = rs.randint(0, npid, nq), rs.randint(0, npid, ng)
+    q_cam, g_cam = rs.randint(0, 4, nq), rs.randint(0, 4, ng)
+    if name == "small_gallery":
+        q_cam[:] = 10                               # no same-camera removals: the reference's numpy path cannot
+                                                    # stack rows shorter than max_rank (rank.py:152 would raise)
+    if name == "ties":
+        dist = np.round(dist * 8).astype(F32) / 8   # massive ties: only 9 distinct keys
+        dist[:, :50] = 2.0                          # the "-1 -> max+1" plateau of distance.py:173-176
+    if name == "some_invalid":
+        q_pids[:5] = 1000                           # identities absent from the gallery
+        sel = g_pids == q_pids[7]
+        g_cam[sel] = q_cam[7]                       # only same-camera matches -> query skipped (rank.py:131-133)
+    return dict(dist=dist, q_pids=q_pids.astype(np.int64), g_pids=g_pids.astype(np.int64),
+                q_camids=q_cam.astype(np.int64), g_camids=g_cam.astype(np.int64), max_rank=max_rank)
+
+
+MODEL_CASES = ["hrnet32_k5", "resnet50_k5", "ibn_k8"]
+_MODEL_SPECS = {"hrnet32_k5": ("hrnet32", 5, 100), "resnet50_k5": ("resnet50", 5, 200), "ibn_k8": ("fastreid_resnet_ibn", 8, 300)}
+
+
+class _Cfg(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def make_cfg(backbone="hrnet32", parts_num=5, **over):
+    """cfg.model.bpbreid node with the reference's defaults (torchreid/scripts/default_config.py:45-58)."""
+    b = _Cfg(pooling="gwap", normalization="identity", mask_filtering_training=False, mask_filtering_testing=True,
+             last_stride=1, dim_reduce="after_pooling", dim_reduce_output=512, backbone=backbone,
+             learnable_attention_enabled=True, test_embeddings=["bn_foreg", "parts"],
+             test_use_target_segmentation="none", training_binary_visibility_score=True,
+             testing_binary_visibility_score=True, shared_parts_id_classifier=False, hrnet_pretrained_path="",
+             masks=_Cfg(parts_num=parts_num))
+    b.update(over)
+    return _Cfg(model=_Cfg(bpbreid=b))
+
+
+def build_product_model(backbone, K, num_classes=751, **over):
+    from bpbreid_b200 import models
+    torch.manual_seed(1234)
+    return models.build_model("bpbreid", num_classes=num_classes, loss="part_based", pretrained=False, use_gpu=False,
+                              config=make_cfg(backbone, K, **over))
+
+
+def model_case(name, n=4, h=256, w=128, num_classes=751):
+    from bpbreid_b200 import params
+    backbone, K, seed = _MODEL_SPECS[name]
+    m = build_product_model(backbone, K, num_classes)
+    sd = params.seeded_state_dict(m, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    images = torch.randn(n, 3, h, w, generator=g).numpy()
+    pids = (np.arange(n) // 2).astype(np.int64)
+    return dict(backbone=backbone, K=K, num_classes=num_classes, state_dict=sd, images=images, pids=pids, model=m)

@@ -1,0 +1,258 @@
+"""GPU (B200): parity of the reference-facing API (bpbreid_b200.models / losses / metrics) against the CPU oracle
+and the golden vectors minted from the reference, plus size-independent properties at BASELINE.json's full
+evaluation size.  Everything goes through the C ABI of libbpbreid_sm100.so."""
+import numpy as np
+import pytest
+import torch
+
+from bpbreid_b200 import losses, metrics
+from oracle import loss_oracle as LO
+from oracle import metrics_oracle as MO
+from oracle import model_oracle as MDL
+from tests import golden_inputs as GI
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(d):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).to(DEV) for k, v in d.items()}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+
+
+# ------------------------------------------------------------------------------------------ GiLt loss
+@pytest.mark.parametrize("name", GI.LOSS_CASES)
+def test_gilt_loss_matches_reference_golden_and_oracle(golden, name):
+    g = golden("losses")
+    c = GI.loss_case(name)
+    crit = losses.GiLtLoss(c["weights"], use_visibility_scores=c["use_vis"], triplet_margin=c["margin"],
+                           loss_name="part_averaged_triplet_loss", use_gpu=True, writer=None)
+    loss, summary = crit(cu(c["emb"]), cu(c["vis"]), cu(c["ids"]), torch.from_numpy(c["pids"]).to(DEV))
+    torch.cuda.synchronize()
+    o_loss, o_sum = LO.gilt(c["emb"], c["vis"], c["ids"], c["pids"], c["weights"], c["use_vis"], c["margin"])
+    assert abs(float(loss) - float(g[f"{name}/loss"])) <= 1e-3 * abs(float(g[f"{name}/loss"]))     # reference
+    assert abs(float(loss) - float(o_loss)) <= 1e-3 * abs(float(o_loss))                             # oracle
+    for key, info in summary.items():
+        for kk, vv in info.items():
+            ref = float(g[f"{name}/{key}/{kk}"])
+            assert abs(float(vv) - ref) <= 1e-3 * max(abs(ref), 1e-3), (key, kk, float(vv), ref)
+    # mining internals: hardest positive / negative indices are integer results -> exact vs the oracle
+    tl = crit.part_triplet_loss.last
+    e = c["emb"]["parts"].transpose(1, 0, 2)
+    pd = LO.part_pairwise_dist(e)
+    if c["use_vis"]:
+        v = c["vis"]["parts"].T
+        m = (v[:, None, :] & v[:, :, None]) if v.dtype == bool else np.sqrt(v[:, None, :] * v[:, :, None])
+        dist = LO.masked_mean(pd, m)
+    else:
+        dist = pd.mean(0, dtype=np.float32)
+    d_gpu = tl["dist"].cpu().numpy()
+    assert np.abs(d_gpu - dist).max() < 2e-3          # sqrt near duplicates
+    assert ((d_gpu == -1) == (dist == -1)).all()      # sentinel pattern identical
+
+
+def test_triplet_no_valid_triplet_returns_none_with_warning():
+    emb = torch.randn(6, 3, 16, device=DEV)
+    pids = torch.arange(6, device=DEV)                # all singletons -> no positive anywhere
+    res = losses.PartAveragedTripletLoss(0.3)(emb, pids)
+    with pytest.warns(UserWarning, match="no valid triplets"):
+        assert res.materialize() is None
+
+
+def test_body_part_attention_loss(golden):
+    g = golden("losses")
+    crit = losses.BodyPartAttentionLoss("cl", 0.1)
+    loss, summary = crit.forward_from_masks(torch.from_numpy(g["bpa/logits"]).to(DEV), torch.from_numpy(g["bpa/masks"]).to(DEV))
+    assert abs(float(loss) - float(g["bpa/loss"])) < 1e-3 * float(g["bpa/loss"])
+    assert abs(float(summary["pixls"]["a"]) - float(g["bpa/acc"])) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ distance
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "simt"])
+@pytest.mark.parametrize("name", GI.DIST_CASES)
+def test_part_distance_matches_reference_golden(golden, name, impl):
+    g = golden("distance")
+    c = GI.distance_case(name)
+    t = lambda a: None if a is None else torch.from_numpy(a).to(DEV)  # noqa: E731
+    d, pd = metrics.part_distance_device(t(c["qf"]), t(c["gf"]), t(c["qv"]), t(c["gv"]), c["strat"], c["metric"], impl)
+    torch.cuda.synchronize()
+    d, pd = d.cpu().numpy(), pd.cpu().numpy()
+    rd, rpd = g[f"{name}/dist"], g[f"{name}/part_dist"]
+    # sentinel (max+1) pattern is an exact property; values within 1e-3 (fp32) -- tf32 dot products keep 10 mantissa bits
+    tol = 2e-3 if impl == 0 else 2e-3
+    assert np.abs(pd - rpd).max() < tol * max(1.0, np.abs(rpd).max()), np.abs(pd - rpd).max()
+    assert np.abs(d - rd).max() < tol * max(1.0, np.abs(rd).max()), np.abs(d - rd).max()
+    if c["qv"] is not None and c["qv"].dtype == bool:
+        inv = ~(c["qv"].T[:, :, None] & c["gv"].T[:, None, :])
+        mv = pd[inv]
+        assert (mv == mv.flat[0]).all() if mv.size else True          # one common max+1 value
+        assert (pd[~inv] < mv.flat[0]).all() if mv.size else True
+
+
+def test_reference_signature_returns_cpu_tensors(golden):
+    c = GI.distance_case("bool_mean")
+    d, pd = metrics.compute_distance_matrix_using_bp_features(
+        torch.from_numpy(c["qf"]), torch.from_numpy(c["gf"]), torch.from_numpy(c["qv"]), torch.from_numpy(c["gv"]),
+        "mean", 500, True, "euclidean")
+    assert d.device.type == "cpu" and pd.device.type == "cpu" and d.dtype == torch.float32
+    g = golden("distance")
+    assert np.abs(d.numpy() - g["bool_mean/dist"]).max() < 5e-3
+    with pytest.raises(ValueError):
+        metrics.compute_distance_matrix_using_bp_features(torch.zeros(2, 1, 32), torch.zeros(2, 1, 32), metric="l1")
+    with pytest.raises(ValueError):
+        metrics.compute_distance_matrix_using_bp_features(torch.zeros(2, 1, 32), torch.zeros(2, 1, 32),
+                                                          dist_combine_strat="median")
+
+
+# ------------------------------------------------------------------------------------------ ranking
+@pytest.mark.parametrize("name", GI.RANK_CASES)
+def test_rank_bit_exact_vs_reference_stable(golden, name):
+    g = golden("rank")
+    c = GI.rank_case(name)
+    r = metrics.evaluate_rank(c["dist"], c["q_pids"], c["g_pids"], c["q_camids"], c["g_camids"], c["max_rank"])
+    np.testing.assert_array_equal(r["cmc"], g[f"{name}/cmc_stable"])                 # reference numpy path, stable sort
+    assert abs(r["mAP"] - float(g[f"{name}/mAP_stable"])) < 1e-12
+    cmc, m_ap = metrics.evaluate_cy(c["dist"], c["q_pids"], c["g_pids"], c["q_camids"], c["g_camids"], c["max_rank"])
+    np.testing.assert_array_equal(cmc, g[f"{name}/cy_cmc_stable"])                   # reference Cython module
+    assert np.float32(m_ap) == np.float32(g[f"{name}/cy_mAP_stable"])
+    idx = metrics.argsort_rows(torch.from_numpy(c["dist"]).to(DEV)).cpu().numpy()
+    np.testing.assert_array_equal(idx, np.argsort(c["dist"], axis=1, kind="stable"))  # ranking indices: bit-exact
+
+
+def test_rank_asserts_when_no_query_is_valid():
+    d = np.random.RandomState(0).rand(4, 9).astype(np.float32)
+    with pytest.raises(AssertionError, match="do not appear in gallery"):
+        metrics.evaluate_rank(d, np.arange(4) + 100, np.arange(9), np.zeros(4), np.ones(9))
+    with pytest.raises(ValueError):
+        metrics.evaluate_rank(d, np.arange(4), np.arange(9), np.zeros(4), np.ones(9), eval_metric="zz")
+
+
+def test_eval_pipeline_medium_scale_vs_oracle():
+    """1024 q x 4096 g x 6 parts: distance (tcgen05) -> ranking, against the CPU oracle end to end."""
+    rs = np.random.RandomState(0)
+    nq, ng, p, d = 1024, 4096, 6, 512
+    qf = MO.l2_normalize(rs.randn(nq, p, d).astype(np.float32))
+    gf = MO.l2_normalize(rs.randn(ng, p, d).astype(np.float32))
+    qv, gv = rs.rand(nq, p) > 0.15, rs.rand(ng, p) > 0.15
+    qp, gp = rs.randint(0, 400, nq), rs.randint(0, 400, ng)
+    qc, gc = rs.randint(0, 6, nq), rs.randint(0, 6, ng)
+    dist, pd = metrics.part_distance_device(torch.from_numpy(qf).to(DEV), torch.from_numpy(gf).to(DEV),
+                                            torch.from_numpy(qv).to(DEV), torch.from_numpy(gv).to(DEV))
+    od, opd = MO.part_distance(qf, gf, qv, gv)
+    assert np.abs(dist.cpu().numpy() - od).max() < 2e-3
+    assert np.abs(pd.cpu().numpy() - opd).max() < 2e-3
+    # ranking on the IDENTICAL fp32 matrix: exact agreement with the oracle (stable order)
+    dn = dist.cpu().numpy()
+    r = metrics.evaluate_rank(dn, qp, gp, qc, gc, 50)
+    o = MO.eval_market1501(dn, qp, gp, qc, gc, 50)
+    np.testing.assert_array_equal(r["cmc"], o["cmc"])
+    assert abs(r["mAP"] - o["mAP"]) < 1e-12
+    cmc_c, map_c = MO.eval_market1501_c(dn, qp, gp, qc, gc, 50)
+    cmc, m32 = metrics.evaluate_cy(dn, qp, gp, qc, gc, 50)
+    np.testing.assert_array_equal(cmc, cmc_c)
+    assert np.float32(m32) == np.float32(map_c)
+    sub = dist[:64].contiguous()
+    np.testing.assert_array_equal(metrics.argsort_rows(sub).cpu().numpy(), np.argsort(dn[:64], axis=1, kind="stable"))
+
+
+def test_full_size_config5_properties():
+    """BASELINE.json config 5 (4096 q x 16384 g, K=5 -> P=6): properties that need no CPU reference."""
+    gq = torch.Generator(device=DEV).manual_seed(0)
+    nq, ng, p, d = 4096, 16384, 6, 512
+    qf = torch.nn.functional.normalize(torch.randn(nq, p, d, device=DEV, generator=gq), dim=-1)
+    gf = torch.nn.functional.normalize(torch.randn(ng, p, d, device=DEV, generator=gq), dim=-1)
+    gf[:nq] = qf                                           # plant every query in the gallery
+    qv = torch.rand(nq, p, device=DEV, generator=gq) > 0.15
+    gv = torch.rand(ng, p, device=DEV, generator=gq) > 0.15
+    qv[:, 0] = True
+    gv[:nq] = qv                                           # same visibility for the planted copies
+    dist, pd = metrics.part_distance_device(qf, gf, qv, gv)
+    diag = dist[torch.arange(nq), torch.arange(nq)]
+    assert float(diag.abs().max()) < 2e-3                  # d(x, x) == 0 up to tf32 rounding
+    assert int((dist.argmin(1) == torch.arange(nq, device=DEV)).sum()) == nq
+    inv = ~(qv.t()[:, :, None] & gv.t()[:, None, :])
+    sentinel = pd.max()
+    assert bool((pd[inv] == sentinel).all()) and bool((pd[~inv] <= 2.001).all())
+    # visibility-masked mean recomputed from the per-part matrix (checksum of checksums)
+    w = (~inv).float()
+    rec = (torch.where(inv, torch.zeros_like(pd), pd)).sum(0) / w.sum(0).clamp(min=1)
+    ok = w.sum(0) > 0
+    assert float((rec[ok] - dist[ok]).abs().max()) < 1e-4
+    # ranking: planted copy with another camera must be rank-0 for every query -> cmc == 1, mAP == 1
+    pid = torch.arange(ng, device=DEV)
+    pid[:nq] = torch.arange(nq, device=DEV)
+    pid[nq:] += 10 ** 6
+    res = metrics.rank_device(dist, torch.arange(nq), pid.cpu(), torch.zeros(nq), torch.ones(ng), 50)
+    assert int(res["num_valid"]) == nq and float(res["cmc"][0]) == 1.0 and abs(float(res["mAP"]) - 1.0) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------ full model
+def _run_model(name, training, conv_impl="tc"):
+    c = GI.model_case(name)
+    m = c["model"]
+    m.load_state_dict(c["state_dict"])
+    m = m.to(DEV)
+    m.train(training)
+    m.conv_impl = conv_impl
+    x = torch.from_numpy(c["images"]).to(DEV)
+    with torch.no_grad():
+        out = m(x)
+    torch.cuda.synchronize()
+    return c, m, out
+
+
+@pytest.mark.parametrize("name", GI.MODEL_CASES)
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_model_forward_matches_reference_golden(golden, name, mode):
+    g = golden("model_" + name)
+    c, m, (emb, vis, ids, pix, feats, masks) = _run_model(name, mode == "train")
+    # bf16 activations: north_star tolerance 1e-2 on part embeddings; measured against the REFERENCE's outputs
+    errs = {}
+    for k in ("globl", "foreg", "backg", "parts", "conct", "bn_globl", "bn_foreg", "bn_parts", "bn_conct"):
+        ref = g[f"{mode}/emb/{k}"]
+        got = emb[k].float().cpu().numpy()
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        errs[k] = np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-12)
+    assert max(errs.values()) < 3e-2, errs
+    for k in ("globl", "foreg", "parts", "conct"):
+        ref = g[f"{mode}/ids/{k}"]
+        got = ids[k].float().cpu().numpy()
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 3e-2, k
+    assert feats.shape[1] == (1920 if c["backbone"] == "hrnet32" else 2048)
+    fm = feats.float().mean(dim=(2, 3)).cpu().numpy()
+    assert np.linalg.norm(fm - g[f"{mode}/feat_mean"]) / np.linalg.norm(g[f"{mode}/feat_mean"]) < 2e-2
+    np.testing.assert_allclose(pix.cpu().numpy(), g[f"{mode}/pix"], rtol=0, atol=3e-2 * np.abs(g[f"{mode}/pix"]).max() + 1e-4)
+    # visibility is a discrete output: allow a flip only where the top-2 probabilities are within bf16 noise
+    vref = g[f"{mode}/vis/parts"]
+    agree = (vis["parts"].cpu().numpy() == vref).mean()
+    assert agree > 0.9, agree
+    if mode == "train":
+        crit = losses.GiLtLoss(None, use_visibility_scores=False, triplet_margin=0.3, use_gpu=True)
+        loss, _ = crit(emb, vis, ids, torch.from_numpy(c["pids"]).to(DEV))
+        ref = float(g["train/gilt_loss"])
+        assert abs(float(loss) - ref) < 1e-2 * abs(ref), (float(loss), ref)
+
+
+@pytest.mark.parametrize("name", ["hrnet32_k5"])
+def test_model_forward_matches_bf16_emulating_oracle(name):
+    """Same rounding points on the CPU (oracle quant hook) -> isolates kernel bugs from bf16 noise."""
+    c, m, (emb, vis, ids, pix, feats, masks) = _run_model(name, True)
+    with torch.no_grad():
+        o = MDL.bpbreid_forward(c["state_dict"], torch.from_numpy(c["images"]), c["backbone"], c["K"], training=True,
+                                quant=MDL.bf16_round)
+    for k in ("globl", "foreg", "parts"):
+        ref = o[0][k].numpy()
+        got = emb[k].float().cpu().numpy()
+        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert err < 2e-2, (k, err)
+
+
+def test_tc_and_reference_conv_paths_agree_on_full_model():
+    _, _, out_tc = _run_model("hrnet32_k5", True, "tc")
+    _, _, out_ref = _run_model("hrnet32_k5", True, "ref")
+    a, b = out_tc[0]["parts"].float().cpu().numpy(), out_ref[0]["parts"].float().cpu().numpy()
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 2e-2

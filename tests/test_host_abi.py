@@ -1,0 +1,67 @@
+"""CPU: host-side logic and the C ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from bpbreid_b200 import _lib, losses, metrics, models
+from tests import golden_inputs as GI
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "build the library first: python -m bpbreid_b200.build"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _lib.header_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(_lib._SIGS) | {"bpb_last_error", "bpb_abi_version"} == set(syms)
+    loaded = _lib.load()
+    assert loaded.bpb_abi_version() == 1
+
+
+def test_model_builder_api_and_errors():
+    with pytest.raises(KeyError):
+        models.build_model("resnet9000", 10)
+    cfg = GI.make_cfg("hrnet32", 5, pooling="nope")
+    with pytest.raises(ValueError):
+        models.build_model("bpbreid", 10, loss="part_based", pretrained=False, config=cfg)
+    with pytest.raises(KeyError):
+        models.build_model("bpbreid", 10, loss="part_based", pretrained=False, config=GI.make_cfg("vgg", 5))
+    m = GI.build_product_model("resnet50", 5, 17)
+    # extra kwargs are swallowed like the reference (models/__init__.py:128-134 always passes use_gpu)
+    assert m.parts_num == 5 and m.num_classes == 17
+    assert m.concat_parts_identity_classifier.classifier.weight.shape == (17, 5 * 512)
+    assert m.global_identity_classifier.bn.bias.requires_grad is False      # bpbreid.py:407
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 3, 256, 128))
+
+
+@pytest.mark.parametrize("backbone,K,nkeys", [("hrnet32", 5, 2022), ("resnet50", 5, 409), ("fastreid_resnet_ibn", 8, 451)])
+def test_state_dict_key_counts(backbone, K, nkeys):
+    # key *names* are checked against the reference in the build container by oracle/make_golden.py
+    # (load_state_dict(strict=True) into the reference model); counts are from SURVEY.md section 8f-1
+    m = GI.build_product_model(backbone, K)
+    assert len(m.state_dict()) == nkeys
+
+
+def test_loss_and_metric_api_errors():
+    with pytest.raises(ValueError):
+        losses.init_part_based_triplet_loss("no_such_loss")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        losses.CrossEntropyLoss()(torch.zeros(4, 10), torch.zeros(4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        losses.PartAveragedTripletLoss()(torch.zeros(4, 2, 8), torch.zeros(4, dtype=torch.long))
+    with pytest.raises(ValueError):
+        losses.BodyPartAttentionLoss(loss_type="zz")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            metrics.evaluate_rank(torch.zeros(2, 3).numpy(), [0, 1], [0, 1, 2], [0, 0], [1, 1, 1])
+
+
+def test_planner_tiling_rule():
+    from bpbreid_b200.plan import _tc_tileable
+    assert _tc_tileable(32, 32, 64, 32) and _tc_tileable(256, 256, 8, 4) and _tc_tileable(64, 64, 16, 8)
+    assert not _tc_tileable(3, 64, 128, 64)
+    assert not _tc_tileable(128, 128, 24, 8)         # 384x128 inputs: 192 px/img does not tile by 128

@@ -1,0 +1,87 @@
+"""CPU: the oracle restatements (oracle/*.py, oracle/rank_oracle.c) against the golden vectors minted from the
+UNMODIFIED reference (oracle/make_golden.py).  This is what pins the oracle (prompt section 3)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_oracle as LO
+from oracle import metrics_oracle as MO
+from oracle import model_oracle as MDL
+from tests import golden_inputs as GI
+
+
+@pytest.mark.parametrize("name", GI.LOSS_CASES)
+def test_gilt_oracle_matches_reference(golden, name):
+    g = golden("losses")
+    c = GI.loss_case(name)
+    loss, summary = LO.gilt(c["emb"], c["vis"], c["ids"], c["pids"], c["weights"], c["use_vis"], c["margin"])
+    np.testing.assert_allclose(loss, g[f"{name}/loss"], rtol=2e-5, atol=1e-6)
+    for key, info in summary.items():
+        for kk, vv in info.items():
+            np.testing.assert_allclose(vv, g[f"{name}/{key}/{kk}"], rtol=2e-5, atol=1e-6, err_msg=f"{key}/{kk}")
+    pd = LO.part_pairwise_dist(c["emb"]["parts"].transpose(1, 0, 2))
+    ref = g[f"{name}/part_pairwise"]
+    np.testing.assert_allclose(pd, ref, rtol=1e-4, atol=2e-3)      # sqrt amplifies 1-ulp differences near 0
+    assert ((pd == 0) == (ref == 0)).mean() > 0.999
+
+
+def test_body_part_attention_oracle(golden):
+    g = golden("losses")
+    loss, acc = LO.body_part_attention(g["bpa/logits"], g["bpa/masks"])
+    np.testing.assert_allclose(loss, g["bpa/loss"], rtol=1e-5)
+    np.testing.assert_allclose(acc, g["bpa/acc"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", GI.DIST_CASES)
+def test_distance_oracle_matches_reference(golden, name):
+    g = golden("distance")
+    c = GI.distance_case(name)
+    d, pd = MO.part_distance(c["qf"], c["gf"], c["qv"], c["gv"], c["strat"], c["metric"])
+    np.testing.assert_allclose(d, g[f"{name}/dist"], rtol=1e-4, atol=2e-3)   # sqrt of a ~1-ulp d^2 at duplicates
+    np.testing.assert_allclose(pd, g[f"{name}/part_dist"], rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", GI.RANK_CASES)
+def test_rank_oracles_match_reference(golden, name):
+    g = golden("rank")
+    c = GI.rank_case(name)
+    r = MO.eval_market1501(c["dist"], c["q_pids"], c["g_pids"], c["q_camids"], c["g_camids"], c["max_rank"])
+    # reference numpy path (fp64) with the sort pinned to stable: exact agreement, ties included
+    np.testing.assert_array_equal(r["cmc"], g[f"{name}/cmc_stable"])
+    np.testing.assert_allclose(r["mAP"], g[f"{name}/mAP_stable"], rtol=1e-12)
+    if name != "ties":      # without ties the reference's default (unstable) sort gives the same answer
+        np.testing.assert_array_equal(r["cmc"], g[f"{name}/cmc"])
+        np.testing.assert_allclose(r["mAP"], g[f"{name}/mAP"], rtol=1e-12)
+    cmc_c, map_c = MO.eval_market1501_c(c["dist"], c["q_pids"], c["g_pids"], c["q_camids"], c["g_camids"], c["max_rank"])
+    np.testing.assert_array_equal(cmc_c, g[f"{name}/cy_cmc_stable"])     # C twin == Cython reference, bit for bit
+    assert np.float32(map_c) == np.float32(g[f"{name}/cy_mAP_stable"])
+    np.testing.assert_allclose(cmc_c, r["cmc"], atol=1e-6)
+    np.testing.assert_allclose(map_c, r["mAP"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", GI.MODEL_CASES)
+def test_model_oracle_matches_reference(golden, name):
+    g = golden("model_" + name)
+    c = GI.model_case(name)
+    x = torch.from_numpy(c["images"])
+    for mode in ("train", "eval"):
+        with torch.no_grad():
+            emb, vis, ids, pix, feats, masks = MDL.bpbreid_forward(c["state_dict"], x, c["backbone"], c["K"],
+                                                                   training=(mode == "train"))
+        for k, v in emb.items():
+            ref = g[f"{mode}/emb/{k}"]
+            err = np.abs(v.numpy() - ref).max() / (np.abs(ref).max() + 1e-12)
+            assert err < 2e-3, (mode, k, err)
+        for k, v in ids.items():
+            ref = g[f"{mode}/ids/{k}"]
+            err = np.abs(v.numpy() - ref).max() / (np.abs(ref).max() + 1e-12)
+            assert err < 2e-3, (mode, k, err)
+        for k, v in vis.items():
+            np.testing.assert_array_equal(v.numpy(), g[f"{mode}/vis/{k}"])
+        np.testing.assert_allclose(pix.numpy(), g[f"{mode}/pix"], rtol=1e-3, atol=1e-4)
+        if mode == "train":
+            ne = {k: v.numpy() for k, v in emb.items()}
+            nv = {k: v.numpy() for k, v in vis.items()}
+            ni = {k: v.numpy() for k, v in ids.items()}
+            loss, _ = LO.gilt(ne, nv, ni, c["pids"])
+            np.testing.assert_allclose(loss, g["train/gilt_loss"], rtol=1e-4)
