@@ -166,8 +166,8 @@ int bpb_triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis
                        S(stream));
 }
 int bpb_ce_ls_fwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c,
-                  float eps, float* scratch, float* out2, void* stream) {
-    return ce_ls_fwd(logits, ld, targets, weights, n, c, eps, scratch, out2, S(stream));
+                  float eps, int acc_mode, float* scratch, float* out2, void* stream) {
+    return ce_ls_fwd(logits, ld, targets, weights, n, c, eps, acc_mode, scratch, out2, S(stream));
 }
 int bpb_pixel_ce_fwd(const float* logits_nchw, const float* target_masks, int n, int kp1, int hf, int wf, int hm,
                      int wm, float label_smoothing, float* partial, float* out2, void* stream) {

@@ -32,7 +32,10 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 }
 
 // |x|^2 per (row, part): x [rows, P, D] -> out [P, rows]
-__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ x, int rows, int p, int d,
+// tf32 != 0: square the values the tensor core will actually see (tcgen05 kind::tf32 ignores the low 13 mantissa
+// bits), so that |q|^2 - 2 q.g + |g|^2 is the squared distance between the *truncated* vectors: exact duplicates give
+// ~0 again and the error becomes relative to the distance instead of to the norms.
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ x, int rows, int p, int d, int tf32,
                                                      float* __restrict__ out) {
     const int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -40,7 +43,10 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ x
     const int r = w / p, pp = w % p;
     const float* v = x + (static_cast<int64_t>(r) * p + pp) * d;
     float s = 0.f;
-    for (int i = lane; i < d; i += 32) s += v[i] * v[i];
+    for (int i = lane; i < d; i += 32) {
+        const float t = tf32 ? __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u) : v[i];
+        s += t * t;
+    }
     s = warp_sum(s);
     if (lane == 0) out[static_cast<int64_t>(pp) * rows + r] = s;
 }
@@ -430,12 +436,12 @@ int part_distance(const float* qf, const float* gf, const void* qv, const void* 
     float* qs = scratch + 4;
     float* gs = qs + static_cast<int64_t>(p) * nq;
     init_max_kernel<<<1, 1, 0, stream>>>(scratch);
+    const bool use_tc = impl != 1 && d % 32 == 0;
     if (metric == METRIC_EUCLIDEAN) {
-        sqnorm_kernel<<<ceil_div(static_cast<int64_t>(nq) * p, 8), 256, 0, stream>>>(qf, nq, p, d, qs);
-        sqnorm_kernel<<<ceil_div(static_cast<int64_t>(ng) * p, 8), 256, 0, stream>>>(gf, ng, p, d, gs);
+        sqnorm_kernel<<<ceil_div(static_cast<int64_t>(nq) * p, 8), 256, 0, stream>>>(qf, nq, p, d, use_tc ? 1 : 0, qs);
+        sqnorm_kernel<<<ceil_div(static_cast<int64_t>(ng) * p, 8), 256, 0, stream>>>(gf, ng, p, d, use_tc ? 1 : 0, gs);
         BPB_LAUNCH_CHECK("sqnorm_kernel");
     }
-    const bool use_tc = impl != 1 && d % 32 == 0;
     if (use_tc) {
         CUtensorMap tmQ, tmG;
         uint32_t box[3] = {32, 1, (uint32_t)kDT};

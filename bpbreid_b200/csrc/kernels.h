@@ -57,7 +57,7 @@ int triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis, in
                 float margin, float* dist_nn, float* hp, float* hn, int* hp_idx, int* hn_idx, float* out4,
                 cudaStream_t stream);
 int ce_ls_fwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c, float eps,
-              float* row_loss, float* out2, cudaStream_t stream);
+              int acc_mode, float* row_loss, float* out2, cudaStream_t stream);
 int pixel_ce_fwd(const float* logits_nchw, const float* target_masks, int n, int kp1, int hf, int wf, int hm, int wm,
                  float label_smoothing, float* partial, float* out2, cudaStream_t stream);
 

@@ -201,16 +201,21 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
 }
 
 // out2 = [loss, accuracy]; weights == null -> mean over rows, else sum_i CE_i * w_i / max(sum|w|, 1e-12)
+// acc_mode 1: accuracy over the rows with non-zero weight (the reference drops invisible rows before both the loss
+// and the accuracy when visibility scores are boolean, GiLt_loss.py:112-114)
 __global__ void __launch_bounds__(256) ce_finalize_kernel(const float* row_loss, const float* row_hit,
-                                                          const float* weights, int n, float* out2) {
-    __shared__ float r0[256], r1[256], r2[256];
-    float l = 0.f, h = 0.f, w = 0.f;
+                                                          const float* weights, int n, int acc_mode, float* out2) {
+    __shared__ float r0[256], r1[256], r2[256], r3[256];
+    float l = 0.f, h = 0.f, w = 0.f, cnt = 0.f;
     for (int i = threadIdx.x; i < n; i += 256) {
         const float wi = weights ? weights[i] : 1.f;
         l += row_loss[i] * wi;
         w += fabsf(wi);
-        h += row_hit[i];
+        const float sel = (acc_mode == 1 && wi == 0.f) ? 0.f : 1.f;
+        h += row_hit[i] * sel;
+        cnt += sel;
     }
+    r3[threadIdx.x] = cnt;
     r0[threadIdx.x] = l; r1[threadIdx.x] = h; r2[threadIdx.x] = w;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
@@ -218,21 +223,22 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(const float* row_loss,
             r0[threadIdx.x] += r0[threadIdx.x + s];
             r1[threadIdx.x] += r1[threadIdx.x + s];
             r2[threadIdx.x] += r2[threadIdx.x + s];
+            r3[threadIdx.x] += r3[threadIdx.x + s];
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         out2[0] = weights ? r0[0] / fmaxf(r2[0], 1e-12f) : r0[0] / static_cast<float>(n);
-        out2[1] = r1[0] / static_cast<float>(n);
+        out2[1] = r1[0] / fmaxf(r3[0], 1.f);
     }
 }
 
 int ce_ls_fwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c, float eps,
-              float* row_loss, float* out2, cudaStream_t stream) {
+              int acc_mode, float* row_loss, float* out2, cudaStream_t stream) {
     // row_loss has room for 2*n floats: [loss | hit]
     ce_rows_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(logits, ld, targets, n, c, eps, row_loss, row_loss + n);
     BPB_LAUNCH_CHECK("ce_rows_kernel");
-    ce_finalize_kernel<<<1, 256, 0, stream>>>(row_loss, row_loss + n, weights, n, out2);
+    ce_finalize_kernel<<<1, 256, 0, stream>>>(row_loss, row_loss + n, weights, n, acc_mode, out2);
     BPB_LAUNCH_CHECK("ce_finalize_kernel");
     return 0;
 }

@@ -40,6 +40,10 @@ struct GemmParams {
 
 enum Epi { EPI_RAW_STATS = 0, EPI_F32_BIAS = 1 };
 
+// Persistent, warp-specialised kernel: each CTA walks output tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest so
+// consecutive tiles share their A rows in L2).  The TMA producer runs ahead across tile boundaries through the smem
+// ring, the MMA warp alternates between two TMEM accumulators, and the epilogue warps drain one accumulator while the
+// next tile's MMAs are in flight.
 template <int BN, bool kTf32, int kEpi>
 __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
@@ -48,28 +52,35 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
     const int a_bytes = kTileM * p.row_bytes;
     const int b_bytes = BN * p.row_bytes;
     const int stage_bytes = a_bytes + b_bytes;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int m_tiles = (p.M + kTileM - 1) / kTileM;
+    const int total_tiles = m_tiles * n_tiles;
+    constexpr int kPitch = BN * 2 + 16;                        // epilogue staging tile row pitch (bytes)
+    uint8_t* epi_tile = smem + p.stages * stage_bytes;         // [128][kPitch], RAW_STATS only
 
-    __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+    __shared__ uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float red_smem[2][4][BN < 64 ? 64 : BN];   // [sum|sq][group][col] (only first 128/(BN/2) groups used)
+    __shared__ float red_smem[2][8][BN < 32 ? 32 : BN];        // [sum|sq][row group][col]
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(&tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 128);
+        }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
     }
-    if (warp == 1) tmem_alloc<BN>(&tmem_base_smem);
+    if (warp == 1) tmem_alloc<2 * BN>(&tmem_base_smem);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -78,164 +89,165 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
-            int n0 = 0, h0 = 0;
-            if (p.mode == 0) {
-                const int hw = p.Ho * p.Wo;
-                const int p0 = m_tile * kTileM;
-                n0 = p0 / hw;
-                h0 = (p0 % hw) / p.Wo;
-            }
-            for (int it = 0; it < p.k_iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t round = it / p.stages;
-                mbar_wait(&empty_bar[s], (round & 1) ^ 1);
-                uint8_t* a_dst = smem + s * stage_bytes;
-                uint8_t* b_dst = a_dst + a_bytes;
-                mbar_expect_tx(&full_bar[s], stage_bytes);
-                const int tap = it / p.kchunks, kcidx = it % p.kchunks;
+            uint32_t g = 0;                                     // global k-iteration counter (ring position)
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m_tile = t / n_tiles, n_tile = t % n_tiles;
+                int n0 = 0, h0 = 0;
                 if (p.mode == 0) {
-                    const int r = tap / p.ksize, sx = tap % p.ksize;
-                    tma_load_4d(a_dst, &tmA, &full_bar[s], kcidx * p.kc, sx - p.pad, h0 * p.stride + r - p.pad, n0);
-                } else if (p.mode == 1) {
-                    tma_load_2d(a_dst, &tmA, &full_bar[s], kcidx * p.kc, m_tile * kTileM);
-                } else {
-                    tma_load_3d(a_dst, &tmA, &full_bar[s], (kcidx % p.dchunks) * p.kc, m_tile * kTileM,
-                                kcidx / p.dchunks);
+                    const int hw = p.Ho * p.Wo;
+                    const int p0 = m_tile * kTileM;
+                    n0 = p0 / hw;
+                    h0 = (p0 % hw) / p.Wo;
                 }
-                tma_load_2d(b_dst, &tmB, &full_bar[s], tap * p.cin + kcidx * p.kc, n_tile * BN);
+                for (int it = 0; it < p.k_iters; ++it, ++g) {
+                    const int s = g % p.stages;
+                    const uint32_t round = g / p.stages;
+                    mbar_wait(&empty_bar[s], (round & 1) ^ 1);
+                    uint8_t* a_dst = smem + s * stage_bytes;
+                    uint8_t* b_dst = a_dst + a_bytes;
+                    mbar_expect_tx(&full_bar[s], stage_bytes);
+                    const int tap = it / p.kchunks, kcidx = it % p.kchunks;
+                    if (p.mode == 0) {
+                        const int r = tap / p.ksize, sx = tap % p.ksize;
+                        tma_load_4d(a_dst, &tmA, &full_bar[s], kcidx * p.kc, sx - p.pad, h0 * p.stride + r - p.pad, n0);
+                    } else if (p.mode == 1) {
+                        tma_load_2d(a_dst, &tmA, &full_bar[s], kcidx * p.kc, m_tile * kTileM);
+                    } else {
+                        tma_load_3d(a_dst, &tmA, &full_bar[s], (kcidx % p.dchunks) * p.kc, m_tile * kTileM,
+                                    kcidx / p.dchunks);
+                    }
+                    tma_load_2d(b_dst, &tmB, &full_bar[s], tap * p.cin + kcidx * p.kc, n_tile * BN);
+                }
             }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
         constexpr uint32_t idesc = make_idesc(kTf32, kTileM, BN);
-        const int k_per_instr_bytes = 32;                    // 16 bf16 or 8 tf32
-        const int instrs = p.row_bytes / k_per_instr_bytes;
-        for (int it = 0; it < p.k_iters; ++it) {
-            const int s = it % p.stages;
-            const uint32_t round = it / p.stages;
-            mbar_wait(&full_bar[s], round & 1);
+        const int instrs = p.row_bytes / 32;                   // 32 bytes of K per instruction (16 bf16 / 8 tf32)
+        uint32_t g = 0, lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1, use = lt >> 1;
+            mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-                const uint32_t b_addr = a_addr + a_bytes;
-                const uint64_t da = make_kmajor_desc(a_addr, p.row_bytes);
-                const uint64_t db = make_kmajor_desc(b_addr, p.row_bytes);
-                for (int k = 0; k < instrs; ++k) {
-                    const uint64_t adv = static_cast<uint64_t>((k * k_per_instr_bytes) >> 4);
-                    umma<kTf32>(tmem_base, da + adv, db + adv, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int it = 0; it < p.k_iters; ++it, ++g) {
+                const int s = g % p.stages;
+                const uint32_t round = g / p.stages;
+                mbar_wait(&full_bar[s], round & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                    const uint64_t da = make_kmajor_desc(a_addr, p.row_bytes);
+                    const uint64_t db = make_kmajor_desc(a_addr + a_bytes, p.row_bytes);
+                    for (int k = 0; k < instrs; ++k)
+                        umma<kTf32>(tmem_base + buf * BN, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);                // smem slot free once these MMAs retire
+                    if (it == p.k_iters - 1) umma_commit(&acc_full[buf]);
                 }
-                umma_commit(&empty_bar[s]);                  // smem slot free once these MMAs retire
-                if (it == p.k_iters - 1) umma_commit(&tmem_full_bar);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ------------------------------ epilogue (warps 2..5) ------------------------------
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;          // row of the tile == output pixel
         const int et = (warp - 2) * 32 + lane;  // 0..127 epilogue thread id
-        const int m0 = m_tile * kTileM, c_base = n_tile * BN;
-        const int valid_rows = min(kTileM, p.M - m0);
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        uint32_t lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int m_tile = t / n_tiles, n_tile = t % n_tiles;
+            const uint32_t buf = lt & 1, use = lt >> 1;
+            const int m0 = m_tile * kTileM, c_base = n_tile * BN;
+            const int valid_rows = min(kTileM, p.M - m0);
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
 
-        if constexpr (kEpi == EPI_F32_BIAS) {
-            float* out = reinterpret_cast<float*>(p.out);
+            if constexpr (kEpi == EPI_F32_BIAS) {
+                float* out = reinterpret_cast<float*>(p.out);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld_wait();
-                if (row < valid_rows) {
-                    float* dst = out + static_cast<size_t>(m0 + row) * p.ldo + c_base + c0;
-                    if (c_base + c0 + 32 <= p.N) {
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (c0 + 32 >= BN) {                        // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        mbar_arrive(&acc_empty[buf]);
+                    }
+                    if (row < valid_rows) {
+                        float* dst = out + static_cast<size_t>(m0 + row) * p.ldo + c_base + c0;
+                        if (c_base + c0 + 32 <= p.N) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o;
-                            o.x = __uint_as_float(v[j + 0]) + (p.bias ? p.bias[c_base + c0 + j + 0] : 0.f);
-                            o.y = __uint_as_float(v[j + 1]) + (p.bias ? p.bias[c_base + c0 + j + 1] : 0.f);
-                            o.z = __uint_as_float(v[j + 2]) + (p.bias ? p.bias[c_base + c0 + j + 2] : 0.f);
-                            o.w = __uint_as_float(v[j + 3]) + (p.bias ? p.bias[c_base + c0 + j + 3] : 0.f);
-                            *reinterpret_cast<float4*>(dst + j) = o;
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 o;
+                                o.x = __uint_as_float(v[j + 0]) + (p.bias ? p.bias[c_base + c0 + j + 0] : 0.f);
+                                o.y = __uint_as_float(v[j + 1]) + (p.bias ? p.bias[c_base + c0 + j + 1] : 0.f);
+                                o.z = __uint_as_float(v[j + 2]) + (p.bias ? p.bias[c_base + c0 + j + 2] : 0.f);
+                                o.w = __uint_as_float(v[j + 3]) + (p.bias ? p.bias[c_base + c0 + j + 3] : 0.f);
+                                *reinterpret_cast<float4*>(dst + j) = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c_base + c0 + j < p.N)
+                                    dst[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[c_base + c0 + j] : 0.f);
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c_base + c0 + j < p.N)
-                                dst[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[c_base + c0 + j] : 0.f);
                     }
                 }
-            }
-        } else {
-            // bf16 tile staged in (now idle) pipeline smem: [128][BN] with a 16-byte row pad
-            constexpr int kPitch = BN * 2 + 16;
-            uint8_t* tile = smem;
+            } else {
+                // previous tile's readers of the staging buffer must be done before it is overwritten
+                asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld_wait();
-                uint4* dst = reinterpret_cast<uint4*>(tile + row * kPitch + c0 * 2);
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (c0 + 32 >= BN) {
+                        tc_fence_before();
+                        mbar_arrive(&acc_empty[buf]);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(epi_tile + row * kPitch + c0 * 2);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 o;
-                    o.x = pack_bf16(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-                    o.y = pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-                    o.z = pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-                    o.w = pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-                    dst[j] = o;
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                        o.y = pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                        o.z = pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                        o.w = pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                        dst[j] = o;
+                    }
                 }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // ---- per-tile column statistics from the bf16-rounded values ----
-            constexpr int kPairs = BN / 2;
-            constexpr int kGroups = (128 / kPairs) < 1 ? 1 : (128 / kPairs);   // BN=32:8, 64:4, 128:2, 256:1
-            if (p.stats != nullptr) {
-                // BN==256: 128 threads each own one channel pair over all rows
-                const int pair = et % kPairs, g = et / kPairs;
-                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                for (int r = g; r < valid_rows; r += kGroups) {
-                    const uint32_t u = *reinterpret_cast<const uint32_t*>(tile + r * kPitch + pair * 4);
-                    const float a = bf16_lo(u), b = bf16_hi(u);
-                    s0 += a; s1 += b; q0 += a * a; q1 += b * b;
-                }
-                if constexpr (kGroups > 4) {
-                    // fold groups g and g+4 first (8 -> 4) through shuffles is not layout friendly; use smem twice
-                    __shared__ float red2[2][8][32];
-                    red2[0][g][pair * 2 + 0] = s0; red2[0][g][pair * 2 + 1] = s1;
-                    red2[1][g][pair * 2 + 0] = q0; red2[1][g][pair * 2 + 1] = q1;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // ---- per-tile column statistics from the bf16-rounded values ----
+                if (p.stats != nullptr) {
+                    constexpr int kPairs = BN / 2;
+                    constexpr int kGroups = 128 / kPairs;                   // BN=32:8, 64:4, 128:2
+                    const int pair = et % kPairs, grp = et / kPairs;
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                    for (int r = grp; r < valid_rows; r += kGroups) {
+                        const uint32_t u = *reinterpret_cast<const uint32_t*>(epi_tile + r * kPitch + pair * 4);
+                        const float a = bf16_lo(u), b = bf16_hi(u);
+                        s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+                    }
+                    red_smem[0][grp][pair * 2 + 0] = s0; red_smem[0][grp][pair * 2 + 1] = s1;
+                    red_smem[1][grp][pair * 2 + 0] = q0; red_smem[1][grp][pair * 2 + 1] = q1;
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (et < BN) {
                         float s = 0.f, qq = 0.f;
 #pragma unroll
-                        for (int gg = 0; gg < 8; ++gg) { s += red2[0][gg][et]; qq += red2[1][gg][et]; }
+                        for (int gg = 0; gg < kGroups; ++gg) { s += red_smem[0][gg][et]; qq += red_smem[1][gg][et]; }
                         float* st = p.stats + static_cast<size_t>(m_tile) * 2 * p.N;
                         st[c_base + et] = s;
                         st[p.N + c_base + et] = qq;
                     }
-                } else {
-                    red_smem[0][g][pair * 2 + 0] = s0; red_smem[0][g][pair * 2 + 1] = s1;
-                    red_smem[1][g][pair * 2 + 0] = q0; red_smem[1][g][pair * 2 + 1] = q1;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    for (int c = et; c < BN; c += 128) {
-                        float s = 0.f, qq = 0.f;
-#pragma unroll
-                        for (int gg = 0; gg < kGroups; ++gg) { s += red_smem[0][gg][c]; qq += red_smem[1][gg][c]; }
-                        float* st = p.stats + static_cast<size_t>(m_tile) * 2 * p.N;
-                        st[c_base + c] = s;
-                        st[p.N + c_base + c] = qq;
-                    }
                 }
-            }
-            // ---- coalesced 16-byte stores of the tile ----
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-            constexpr int kChunksPerRow = BN / 8;
-            for (int ch = et; ch < kTileM * kChunksPerRow; ch += 128) {
-                const int r = ch / kChunksPerRow, cc = ch % kChunksPerRow;
-                if (r < valid_rows) {
-                    const uint4 o = *reinterpret_cast<const uint4*>(tile + r * kPitch + cc * 16);
-                    *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + r) * p.ldo + c_base + cc * 8) = o;
+                // ---- coalesced 16-byte stores of the tile ----
+                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+                constexpr int kChunksPerRow = BN / 8;
+                for (int ch = et; ch < kTileM * kChunksPerRow; ch += 128) {
+                    const int r = ch / kChunksPerRow, cc = ch % kChunksPerRow;
+                    if (r < valid_rows) {
+                        const uint4 o = *reinterpret_cast<const uint4*>(epi_tile + r * kPitch + cc * 16);
+                        *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + r) * p.ldo + c_base + cc * 8) = o;
+                    }
                 }
             }
         }
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem_base);
+        tmem_dealloc<2 * BN>(tmem_base);
     }
 }
 
@@ -254,27 +266,34 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
 template <int BN, bool kTf32, int kEpi>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     const int stage_bytes = (kTileM + BN) * p.row_bytes;
-    size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024;
-    const size_t epi = static_cast<size_t>(kTileM) * (BN * 2 + 16) + 1024;
-    if (kEpi == EPI_RAW_STATS && smem < epi) smem = epi;
+    const size_t epi = kEpi == EPI_RAW_STATS ? static_cast<size_t>(kTileM) * (BN * 2 + 16) : 0;
+    const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + epi + 1024;
     auto kern = tc_gemm_kernel<BN, kTf32, kEpi>;
     static bool configured = false;
     if (!configured) {
         BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    dim3 grid((p.M + kTileM - 1) / kTileM, (p.N + BN - 1) / BN);
+    const int total = ((p.M + kTileM - 1) / kTileM) * ((p.N + BN - 1) / BN);
+    // persistent: as many CTAs as fit per SM (smem and TMEM: 2*BN columns each), but never more than tiles
+    int per_sm = static_cast<int>((220 * 1024) / (smem + 2048));
+    if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm < 1) per_sm = 1;
+    int grid = 148 * per_sm;
+    if (grid > total) grid = total;
     kern<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, p);
     BPB_LAUNCH_CHECK("tc_gemm_kernel");
     return 0;
 }
 
 static int pick_stages(int bn, int row_bytes, int k_iters) {
+    // ring depth: ~64 KB of operands in flight per CTA (the ring spans tile boundaries in the persistent kernel)
     const int stage_bytes = (kTileM + bn) * row_bytes;
-    int s = (96 * 1024) / stage_bytes;
+    int s = (64 * 1024) / stage_bytes;
     if (s > 8) s = 8;
-    if (s > k_iters) s = k_iters;
-    if (s < 2) s = 2;
+    if (s < 3) s = 3;
+    (void)k_iters;
     return s;
 }
 

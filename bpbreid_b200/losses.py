@@ -118,7 +118,7 @@ class CrossEntropyLoss(nn.Module):
         self.eps = eps if label_smooth else 0
         self.last_accuracy = None
 
-    def forward(self, inputs, targets, weights=None):
+    def forward(self, inputs, targets, weights=None, acc_over_weighted_rows=False):
         _need_cuda(inputs, "CrossEntropyLoss")
         assert inputs.shape[0] == targets.shape[0]
         n, c = inputs.shape
@@ -131,7 +131,7 @@ class CrossEntropyLoss(nn.Module):
         scratch = torch.empty(2 * n, device=inputs.device)
         out2 = torch.empty(2, device=inputs.device)
         _lib.call("bpb_ce_ls_fwd", inputs.data_ptr(), ld, targets.data_ptr(), _lib.ptr(w), n, c, float(self.eps),
-                  scratch.data_ptr(), out2.data_ptr(), _lib.stream_ptr())
+                  1 if acc_over_weighted_rows else 0, scratch.data_ptr(), out2.data_ptr(), _lib.stream_ptr())
         self.last_accuracy = out2[1]
         return out2[0]
 
@@ -203,14 +203,14 @@ class GiLtLoss(nn.Module):
             id_cls_scores = id_cls_scores.flatten(0, 1)
             pids = pids.unsqueeze(1).expand(-1, m).flatten(0, 1)
             visibility_scores = visibility_scores.flatten(0, 1)
-        weights = None
+        weights, filtered = None, False
         if self.use_visibility_scores and visibility_scores.dtype is torch.bool:
             # reference drops the invisible rows; a {0,1}-weighted mean over all rows is the same number and
             # keeps shapes static (no host sync)
-            weights = visibility_scores.float()
+            weights, filtered = visibility_scores.float(), True
         elif self.use_visibility_scores and visibility_scores.dtype is not torch.bool:
             weights = visibility_scores
-        cls_loss = self.identity_loss(id_cls_scores, pids, weights)
+        cls_loss = self.identity_loss(id_cls_scores, pids, weights, acc_over_weighted_rows=filtered)
         return cls_loss, self.identity_loss.last_accuracy
 
 

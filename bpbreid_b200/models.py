@@ -72,6 +72,7 @@ class BPBreID(nn.Module):
         self._plans = {}
         self.conv_impl = "tc"
         self.use_cuda_graph = False
+        self.debug_trace = False
 
     # -- forward ---------------------------------------------------------------------------------------------
     def plan_for(self, images):
@@ -79,14 +80,15 @@ class BPBreID(nn.Module):
             raise RuntimeError("bpbreid_b200.BPBreID runs on sm_100a only: move the model and the images to a CUDA "
                                "device (there is no CPU fallback path)")
         n, _, h, w = images.shape
-        key = (n, h, w, self.training, images.device.index, self.conv_impl, self.use_cuda_graph)
+        key = (n, h, w, self.training, images.device.index, self.conv_impl, self.use_cuda_graph, self.debug_trace)
         plan = self._plans.get(key)
         if plan is None:
             from .plan import ForwardPlan
             p0 = next(self.parameters())
             if p0.device != images.device:
                 raise RuntimeError(f"model parameters live on {p0.device}, images on {images.device}")
-            plan = ForwardPlan(self, n, h, w, self.training, images.device, self.conv_impl, self.use_cuda_graph)
+            plan = ForwardPlan(self, n, h, w, self.training, images.device, self.conv_impl, self.use_cuda_graph,
+                               self.debug_trace)
             self._plans[key] = plan
         return plan
 

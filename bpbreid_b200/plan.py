@@ -56,7 +56,7 @@ def _tc_tileable(cin, cout, ho, wo):
 
 
 class ForwardPlan:
-    def __init__(self, model, n, h, w, training, device, conv_impl="tc", use_graph=False):
+    def __init__(self, model, n, h, w, training, device, conv_impl="tc", use_graph=False, debug=False):
         self.model = model
         self.n, self.h, self.w = n, h, w
         self.training = bool(training)
@@ -71,6 +71,11 @@ class ForwardPlan:
         self.graph = None
         self.use_graph = use_graph
         self.lib = _lib.load()
+        # debug: keep every intermediate activation alive (no buffer reuse) and record (block, inputs, outputs) so
+        # tests can check each block of the real network against the oracle on the block's actual input
+        self.debug = debug
+        self.trace = []
+        self._names = {id(mod): name for name, mod in model.named_modules()} if debug else {}
         self.cfg = model.model_cfg
         self.K = model.parts_num
         self.images = torch.zeros(n, 3, h, w, device=device, dtype=torch.float32)
@@ -112,10 +117,15 @@ class ForwardPlan:
             mine = self._scopes.pop()
             kept_ids = {id(a.buf) for a in keep}
             for buf in mine:
-                if id(buf) in kept_ids:
+                if self.debug or id(buf) in kept_ids:
                     self._scopes[-1].append(buf)
                 else:
                     self._free.setdefault(buf.numel(), []).append(buf)
+
+    def _trace(self, kind, mods, ins, outs, **extra):
+        if self.debug:
+            names = [self._names.get(id(m), "?") for m in (mods if isinstance(mods, (list, tuple)) else [mods])]
+            self.trace.append(dict(kind=kind, names=names, ins=list(ins), outs=list(outs), **extra))
 
     # ------------------------------------------------------------------ op recording
     def _op(self, name, *args):
@@ -221,6 +231,7 @@ class ForwardPlan:
             a = self.apply(self.conv_bn(x, blk.conv1, blk.bn1), True)
             y = self.apply(self.conv_bn(a, blk.conv2, blk.bn2), True, res=x)
             keep.append(y)
+        self._trace("basic", blk, [x], [y])
         return y
 
     def bottleneck(self, x: Act, blk) -> Act:
@@ -237,6 +248,7 @@ class ForwardPlan:
                 res = x
             y = self.apply(l3, True, res=res)
             keep.append(y)
+        self._trace("bottleneck", blk, [x], [y], stride=blk.stride)
         return y
 
     def ibn_relu(self, x: Act, conv, ibn) -> Act:
@@ -284,7 +296,14 @@ class ForwardPlan:
                  ksize, stride)
         stats, tiles = (self.colstats(raw) if self.training else (None, 0))
         scale, shift = self.bn_scale_shift(stats, tiles, raw.c, raw.m, bn)
-        return self.apply(Lazy(raw, scale, shift), True)
+        y = self.apply(Lazy(raw, scale, shift), True)
+        self._trace("stem", [conv, bn], [], [y], ksize=ksize, stride=stride)
+        return y
+
+    def conv_bn_relu(self, x: Act, conv, bn) -> Act:
+        y = self.apply(self.conv_bn(x, conv, bn), True)
+        self._trace("conv_bn_relu", [conv, bn], [x], [y], stride=conv.stride[0], ksize=conv.kernel_size[0])
+        return y
 
     # ------------------------------------------------------------------ backbones
     def hr_module(self, xs, mod):
@@ -316,25 +335,25 @@ class ForwardPlan:
                                 t = self.apply(lz, True)
                 outs.append(self.fuse(terms, ys[i]))
             keep.extend(outs)
+        self._trace("fuse", mod, ys, outs)
         return outs
 
     def build_hrnet(self, bb):
         with self.scope() as keep:
             x = self.stem(bb.conv1, bb.bn1, 3, 2)
-            x = self.apply(self.conv_bn(x, bb.conv2, bb.bn2), True)
+            x = self.conv_bn_relu(x, bb.conv2, bb.bn2)
             for blk in bb.layer1:
                 x = self.bottleneck(x, blk)
             t = bb.transition1
-            xs = [self.apply(self.conv_bn(x, t[0][0], t[0][1]), True),
-                  self.apply(self.conv_bn(x, t[1][0][0], t[1][0][1]), True)]
+            xs = [self.conv_bn_relu(x, t[0][0], t[0][1]), self.conv_bn_relu(x, t[1][0][0], t[1][0][1])]
             for mod in bb.stage2:
                 xs = self.hr_module(xs, mod)
             t = bb.transition2[2][0]
-            xs = xs + [self.apply(self.conv_bn(xs[-1], t[0], t[1]), True)]
+            xs = xs + [self.conv_bn_relu(xs[-1], t[0], t[1])]
             for mod in bb.stage3:
                 xs = self.hr_module(xs, mod)
             t = bb.transition3[3][0]
-            xs = xs + [self.apply(self.conv_bn(xs[-1], t[0], t[1]), True)]
+            xs = xs + [self.conv_bn_relu(xs[-1], t[0], t[1])]
             for mod in bb.stage4:
                 xs = self.hr_module(xs, mod)
             br = [self.bottleneck(xs[i], bb.incre_modules[i][0]) for i in range(4)]
@@ -343,6 +362,7 @@ class ForwardPlan:
                      self._int_array([b.h for b in br]), self._int_array([b.w for b in br]), 4, feats.t.data_ptr(),
                      self.n, feats.h, feats.w)
             keep.append(feats)
+        self._trace("upcat", [], br, [feats])
         return feats
 
     def build_resnet(self, bb):
@@ -358,6 +378,7 @@ class ForwardPlan:
                 wo -= 1
             y = self._act(x.n, ho, wo, x.c)
             self._op("bpb_maxpool3x3s2", x.t.data_ptr(), y.t.data_ptr(), x.n, x.h, x.w, x.c, pad, ceil)
+            self._trace("maxpool", [], [x], [y], pad=pad, ceil=ceil)
             x = y
             for li in range(1, 5):
                 for blk in getattr(bb, f"layer{li}"):

@@ -106,9 +106,10 @@ int bpb_vis_unpack(const int* vis_bits, const float* vis_cont, int n, int kp1, u
 int bpb_triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
                     float margin, float* dist_nn, float* hp, float* hn, int* hp_idx, int* hn_idx, float* out4,
                     void* stream);
-/* Label-smoothed CE (cross_entropy_loss.py:34-56); scratch has 2n floats; out2 = {loss, top-1 accuracy}. */
+/* Label-smoothed CE (cross_entropy_loss.py:34-56); scratch has 2n floats; out2 = {loss, top-1 accuracy}.
+ * weights NULL: mean over rows; else sum_i CE_i w_i / |w|_1.  acc_mode 1: accuracy over rows with w != 0. */
 int bpb_ce_ls_fwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c,
-                  float eps, float* scratch, float* out2, void* stream);
+                  float eps, int acc_mode, float* scratch, float* out2, void* stream);
 /* Body part attention loss (part_based_engine.py:118-124 + body_part_attention_loss.py:31-52);
  * partial has 512 floats; out2 = {loss, pixel accuracy}. */
 int bpb_pixel_ce_fwd(const float* logits_nchw, const float* target_masks, int n, int kp1, int hf, int wf, int hm,
