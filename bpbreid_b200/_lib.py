@@ -20,6 +20,8 @@ _F = ctypes.c_float
 _SIGS = {
     "bpb_conv_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpb_conv_num_mtiles": [_I, _I, _I],
+    "bpb_conv_bn_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I, _P, _P, _P],
+    "bpb_conv_bn_workspace_bytes": [_I],
     "bpb_conv_ref_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpb_stem_conv": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bpb_colstats_bf16": [_P, _P, _I, _I, _P],
@@ -72,7 +74,7 @@ def load():
     for name, sig in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = sig
-        fn.restype = _L if name == "bpb_part_distance_scratch_floats" else _I
+        fn.restype = _L if name in ("bpb_part_distance_scratch_floats", "bpb_conv_bn_workspace_bytes") else _I
     _lib = lib
     return lib
 

@@ -79,8 +79,16 @@ int bpb_abi_version(void) { return 1; }
 
 int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                   int ksize, int stride, int bn_hint, void* stream) {
-    return conv_bf16_tc(x, w, y, stats, n, h, wd, cin, cout, ksize, stride, bn_hint, S(stream));
+    return conv_bf16_tc(x, w, y, stats, n, h, wd, cin, cout, ksize, stride, bn_hint, nullptr, S(stream));
 }
+int bpb_conv_bn_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
+                     int ksize, int stride, int bn_hint, void* bn_workspace, const float* gamma, const float* beta,
+                     float eps, float momentum, float* running_mean, float* running_var, int c_lo, float* scale,
+                     float* shift, void* stream) {
+    BnFuse bn{bn_workspace, gamma, beta, running_mean, running_var, scale, shift, eps, momentum, c_lo};
+    return conv_bf16_tc(x, w, y, stats, n, h, wd, cin, cout, ksize, stride, bn_hint, &bn, S(stream));
+}
+int64_t bpb_conv_bn_workspace_bytes(int cout) { return static_cast<int64_t>(cout) * 2 * 8 + 16; }
 int bpb_conv_num_mtiles(int n, int ho, int wo) { return conv_num_mtiles(n, ho, wo); }
 int bpb_conv_ref_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize,
                       int stride, void* stream) {

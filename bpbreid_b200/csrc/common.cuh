@@ -97,9 +97,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded spin: a descriptor/pipeline bug must surface as a trap (-> CUDA error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > 20000000u) {
+        if (clock64() - t0 > 4000000000ll) {      // ~2 s of SM clocks: pipeline bug, not load
             printf("bpb: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z,
                    threadIdx.x);
             __trap();

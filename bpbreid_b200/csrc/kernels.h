@@ -7,8 +7,17 @@
 namespace bpb {
 
 // ---- tc_gemm.cu -------------------------------------------------------------------------------
+// Train-mode BatchNorm fused into the convolution launch (last CTA finalizes): see GemmParams in tc_gemm.cu.
+struct BnFuse {
+    void* workspace;            // 2*cout doubles + 1 uint32 (zero-initialised once; the kernel leaves it zeroed)
+    const float* gamma; const float* beta;
+    float* running_mean; float* running_var;
+    float* scale; float* shift;
+    float eps, momentum;
+    int c_lo;                   // parameters cover channels [c_lo, cout) (IBN: first half is instance-normalised)
+};
 int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
-                 int ksize, int stride, int bn_hint, cudaStream_t stream);
+                 int ksize, int stride, int bn_hint, const BnFuse* bn, cudaStream_t stream);
 int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bias, float* out, int m, int n, int k,
                    int ldo, int a_mode, int a_parts, cudaStream_t stream);
 int conv_num_mtiles(int n, int ho, int wo);

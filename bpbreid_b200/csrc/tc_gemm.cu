@@ -34,8 +34,19 @@ struct GemmParams {
     int ksize, stride, pad, Ho, Wo;
     int ldo;        // output leading dimension (elements)
     void* out;
-    float* stats;   // [m_tiles, 2, N] per-tile column sum / sum of squares (EPI_RAW_STATS)
+    float* stats;   // optional [m_tiles, 2, N] per-tile column sum / sum of squares (EPI_RAW_STATS)
     const float* bias;
+    // fused train-mode BatchNorm finalize (EPI_RAW_STATS, bn_acc != null): every CTA adds its column sums to
+    // bn_acc[2][N] (fp64 atomics); the last CTA to finish turns them into scale/shift, updates the running
+    // statistics and leaves bn_acc / bn_counter zeroed for the next launch.
+    double* bn_acc;
+    unsigned int* bn_counter;
+    const float* gamma; const float* beta;
+    float* running_mean; float* running_var;
+    float* scale; float* shift;
+    float eps, momentum;
+    double inv_count, unbias;
+    int c_lo;
 };
 
 enum Epi { EPI_RAW_STATS = 0, EPI_F32_BIAS = 1 };
@@ -60,6 +71,10 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     const int total_tiles = m_tiles * n_tiles;
     constexpr int kPitch = BN * 2 + 16;                        // epilogue staging tile row pitch (bytes)
     uint8_t* epi_tile = smem + p.stages * stage_bytes;         // [128][kPitch], RAW_STATS only
+    float* cta_stats = reinterpret_cast<float*>(epi_tile + kTileM * kPitch);   // [2][N] CTA-level column sums
+    const bool fused_bn = kEpi == EPI_RAW_STATS && p.bn_acc != nullptr;
+    if (fused_bn)
+        for (int i = threadIdx.x; i < 2 * p.N; i += kNumThreads) cta_stats[i] = 0.f;
 
     __shared__ uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
@@ -217,7 +232,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 // ---- per-tile column statistics from the bf16-rounded values ----
-                if (p.stats != nullptr) {
+                if (p.stats != nullptr || fused_bn) {
                     constexpr int kPairs = BN / 2;
                     constexpr int kGroups = 128 / kPairs;                   // BN=32:8, 64:4, 128:2
                     const int pair = et % kPairs, grp = et / kPairs;
@@ -234,9 +249,15 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                         float s = 0.f, qq = 0.f;
 #pragma unroll
                         for (int gg = 0; gg < kGroups; ++gg) { s += red_smem[0][gg][et]; qq += red_smem[1][gg][et]; }
-                        float* st = p.stats + static_cast<size_t>(m_tile) * 2 * p.N;
-                        st[c_base + et] = s;
-                        st[p.N + c_base + et] = qq;
+                        if (p.stats != nullptr) {
+                            float* st = p.stats + static_cast<size_t>(m_tile) * 2 * p.N;
+                            st[c_base + et] = s;
+                            st[p.N + c_base + et] = qq;
+                        }
+                        if (fused_bn) {                          // owner thread of this column: no race
+                            cta_stats[c_base + et] += s;
+                            cta_stats[p.N + c_base + et] += qq;
+                        }
                     }
                 }
                 // ---- coalesced 16-byte stores of the tile ----
@@ -248,6 +269,46 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                         const uint4 o = *reinterpret_cast<const uint4*>(epi_tile + r * kPitch + cc * 16);
                         *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + r) * p.ldo + c_base + cc * 8) = o;
                     }
+                }
+            }
+        }
+        if constexpr (kEpi == EPI_RAW_STATS) {
+            if (fused_bn) {
+                __shared__ int s_is_last;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = et; c < 2 * p.N; c += 128) {
+                    const float v = cta_stats[c];
+                    if (v != 0.f) atomicAdd(p.bn_acc + c, static_cast<double>(v));
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    const unsigned prev = atomicAdd(p.bn_counter, 1u);
+                    s_is_last = prev == gridDim.x - 1;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (s_is_last) {
+                    __threadfence();
+                    for (int ch = et; ch < p.N; ch += 128) {
+                        const double sum = __ldcg(p.bn_acc + ch), sq = __ldcg(p.bn_acc + p.N + ch);
+                        const double mean = sum * p.inv_count;
+                        double var = sq * p.inv_count - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        const int pc = ch - p.c_lo;
+                        const float g = (p.gamma && pc >= 0) ? p.gamma[pc] : 1.f;
+                        const float b = (p.beta && pc >= 0) ? p.beta[pc] : 0.f;
+                        const float sc = g * rsqrtf(static_cast<float>(var) + p.eps);
+                        p.scale[ch] = sc;
+                        p.shift[ch] = b - static_cast<float>(mean) * sc;
+                        if (p.running_mean && pc >= 0)
+                            p.running_mean[pc] = (1.f - p.momentum) * p.running_mean[pc] + p.momentum * static_cast<float>(mean);
+                        if (p.running_var && pc >= 0)
+                            p.running_var[pc] = (1.f - p.momentum) * p.running_var[pc] +
+                                                p.momentum * static_cast<float>(var * p.unbias);
+                        p.bn_acc[ch] = 0.0;
+                        p.bn_acc[p.N + ch] = 0.0;
+                    }
+                    if (et == 0) *p.bn_counter = 0u;
                 }
             }
         }
@@ -266,7 +327,9 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
 template <int BN, bool kTf32, int kEpi>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     const int stage_bytes = (kTileM + BN) * p.row_bytes;
-    const size_t epi = kEpi == EPI_RAW_STATS ? static_cast<size_t>(kTileM) * (BN * 2 + 16) : 0;
+    const size_t epi = kEpi == EPI_RAW_STATS
+                           ? static_cast<size_t>(kTileM) * (BN * 2 + 16) + (p.bn_acc ? 2 * sizeof(float) * p.N : 0)
+                           : 0;
     const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + epi + 1024;
     auto kern = tc_gemm_kernel<BN, kTf32, kEpi>;
     static bool configured = false;
@@ -275,12 +338,20 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
         configured = true;
     }
     const int total = ((p.M + kTileM - 1) / kTileM) * ((p.N + BN - 1) / BN);
-    // persistent: as many CTAs as fit per SM (smem and TMEM: 2*BN columns each), but never more than tiles
-    int per_sm = static_cast<int>((220 * 1024) / (smem + 2048));
+    // persistent: exactly as many CTAs as are co-resident (registers / smem via the occupancy API, TMEM: 2*BN
+    // columns each) -- a static tile assignment must never have a second wave of CTAs
+    int per_sm = 1;
+    BPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNumThreads, smem));
     if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);
-    if (per_sm > 3) per_sm = 3;
+    if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
-    int grid = 148 * per_sm;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        BPB_CUDA(cudaGetDevice(&dev));
+        BPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int grid = num_sms * per_sm;
     if (grid > total) grid = total;
     kern<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, p);
     BPB_LAUNCH_CHECK("tc_gemm_kernel");
@@ -307,7 +378,7 @@ static int pick_bn(int m_tiles, int cout, int bn_hint) {
 
 // NHWC bf16 convolution (ksize 1 or 3, stride 1 or 2, pad = ksize/2), raw bf16 output + per-tile BN partials.
 int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
-                 int ksize, int stride, int bn_hint, cudaStream_t stream) {
+                 int ksize, int stride, int bn_hint, const BnFuse* bn, cudaStream_t stream) {
     const int pad = ksize / 2;
     const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (wd + 2 * pad - ksize) / stride + 1;
     BPB_CHECK(cin % 32 == 0 && cout % 32 == 0, "conv_bf16_tc: channels must be multiples of 32 (cin=%d cout=%d)", cin,
@@ -334,9 +405,21 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     p.out = y;
     p.stats = stats;
     p.bias = nullptr;
+    if (bn != nullptr) {
+        BPB_CHECK(bn->workspace != nullptr && bn->scale != nullptr && bn->shift != nullptr, "conv_bf16_tc: BN outputs");
+        p.bn_acc = reinterpret_cast<double*>(bn->workspace);
+        p.bn_counter = reinterpret_cast<unsigned int*>(p.bn_acc + 2 * static_cast<size_t>(cout));
+        p.gamma = bn->gamma; p.beta = bn->beta;
+        p.running_mean = bn->running_mean; p.running_var = bn->running_var;
+        p.scale = bn->scale; p.shift = bn->shift;
+        p.eps = bn->eps; p.momentum = bn->momentum;
+        p.inv_count = 1.0 / static_cast<double>(p.M);
+        p.unbias = p.M > 1 ? static_cast<double>(p.M) / static_cast<double>(p.M - 1) : 1.0;
+        p.c_lo = bn->c_lo;
+    }
     const int m_tiles = (p.M + kTileM - 1) / kTileM;
-    const int bn = pick_bn(m_tiles, cout, bn_hint);
-    p.stages = pick_stages(bn, p.row_bytes, p.k_iters);
+    const int bn_tile = pick_bn(m_tiles, cout, bn_hint);
+    p.stages = pick_stages(bn_tile, p.row_bytes, p.k_iters);
 
     const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tmA, tmB;
@@ -351,15 +434,15 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
         const uint64_t ktot = (uint64_t)ksize * ksize * cin;
         uint64_t dims[2] = {ktot, (uint64_t)cout};
         uint64_t strides[1] = {ktot * 2};
-        uint32_t box[2] = {(uint32_t)kc, (uint32_t)bn};
+        uint32_t box[2] = {(uint32_t)kc, (uint32_t)bn_tile};
         uint32_t es[2] = {1, 1};
         if (make_tensor_map(&tmB, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, es, sw)) return 4;
     }
-    switch (bn) {
+    switch (bn_tile) {
         case 32: return launch<32, false, EPI_RAW_STATS>(tmA, tmB, p, stream);
         case 64: return launch<64, false, EPI_RAW_STATS>(tmA, tmB, p, stream);
         case 128: return launch<128, false, EPI_RAW_STATS>(tmA, tmB, p, stream);
-        default: BPB_CHECK(false, "conv_bf16_tc: unsupported BN %d", bn);
+        default: BPB_CHECK(false, "conv_bf16_tc: unsupported BN %d", bn_tile);
     }
     return 0;
 }

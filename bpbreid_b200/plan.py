@@ -63,6 +63,7 @@ class ForwardPlan:
         self.device = device
         self.conv_impl = conv_impl
         self.ops = []                 # (ctypes fn, args tuple) ; stream appended at run time
+        self.setup_ops = []           # run once at build / after a weight refresh (eval-mode BN folds)
         self.keepalive = []           # ctypes arrays referenced by ops
         self.persistent = []          # tensors that must outlive the plan build
         self._free = {}               # pooled activation buffers by byte size
@@ -80,6 +81,7 @@ class ForwardPlan:
         self.K = model.parts_num
         self.images = torch.zeros(n, 3, h, w, device=device, dtype=torch.float32)
         self._packed = {}
+        self._need_setup = True
         with torch.no_grad():
             self._build()
 
@@ -132,6 +134,9 @@ class ForwardPlan:
         self.ops.append((getattr(self.lib, name), args, name))
         self.launches += 1
 
+    def _setup_op(self, name, *args):
+        self.setup_ops.append((getattr(self.lib, name), args, name))
+
     def _ptr_array(self, tensors):
         arr = (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
         self.keepalive.append(arr)
@@ -161,6 +166,7 @@ class ForwardPlan:
             if isinstance(mod, nn.Conv2d) and id(mod) in self._packed:
                 w = mod.weight.detach()
                 self._packed[id(mod)].copy_(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))
+        self._need_setup = True      # eval-mode BN folds depend on the (possibly reloaded) running statistics
 
     # ------------------------------------------------------------------ building blocks
     def _bn_params(self, bn, c_lo=0):
@@ -174,9 +180,10 @@ class ForwardPlan:
             self._op("bpb_bn_finalize", stats.data_ptr(), tiles, c, c_lo, count, g.data_ptr(), b.data_ptr(),
                      BN_EPS, float(mom), rm.data_ptr(), rv.data_ptr(), scale.data_ptr(), shift.data_ptr())
         else:
+            # inference: running statistics are constants -> folded once, outside the replayed step
             assert c_lo == 0
-            self._op("bpb_bn_eval_fold", g.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(), BN_EPS, c,
-                     scale.data_ptr(), shift.data_ptr())
+            self._setup_op("bpb_bn_eval_fold", g.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(), BN_EPS, c,
+                           scale.data_ptr(), shift.data_ptr())
         return scale, shift
 
     def conv_raw(self, x: Act, conv: nn.Conv2d, need_stats=True):
@@ -207,9 +214,37 @@ class ForwardPlan:
         self._op("bpb_colstats_bf16", y.t.data_ptr(), stats.data_ptr(), y.m, y.c)
         return stats, tiles
 
-    def conv_bn(self, x: Act, conv, bn) -> Lazy:
+    def conv_bn(self, x: Act, conv, bn, c_lo=0) -> Lazy:
+        """conv + BatchNorm statistics.  Training + tensor-core path: ONE launch (the conv's last CTA finalizes the
+        batch statistics into scale/shift and updates the running stats); otherwise conv, then bn_finalize / fold."""
+        k, s = conv.kernel_size[0], conv.stride[0]
+        cout, pad = conv.out_channels, k // 2
+        ho, wo = (x.h + 2 * pad - k) // s + 1, (x.w + 2 * pad - k) // s + 1
+        if self.training and self.conv_impl == "tc" and _tc_tileable(x.c, cout, ho, wo):
+            y = self._act(x.n, ho, wo, cout)
+            wp = self.pack_conv(conv)
+            ws = torch.zeros(_lib.query("bpb_conv_bn_workspace_bytes", cout), dtype=torch.uint8, device=self.device)
+            self.persistent.append(ws)
+            scale, shift = self._small((cout,)), self._small((cout,))
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            self._op("bpb_conv_bn_bf16", x.t.data_ptr(), wp.data_ptr(), y.t.data_ptr(), None, x.n, x.h, x.w, x.c, cout,
+                     k, s, 0, ws.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS, float(mom),
+                     bn.running_mean.data_ptr(), bn.running_var.data_ptr(), c_lo, scale.data_ptr(), shift.data_ptr())
+            return Lazy(y, scale, shift)
         y, stats, tiles = self.conv_raw(x, conv)
-        scale, shift = self.bn_scale_shift(stats, tiles, y.c, y.m, bn)
+        if c_lo == 0:
+            scale, shift = self.bn_scale_shift(stats, tiles, y.c, y.m, bn)
+        else:
+            scale, shift = self._small((y.c,)), self._small((y.c,))
+            if self.training:
+                mom = bn.momentum if bn.momentum is not None else 0.1
+                self._op("bpb_bn_finalize", stats.data_ptr(), tiles, y.c, c_lo, y.m, bn.weight.data_ptr(),
+                         bn.bias.data_ptr(), BN_EPS, float(mom), bn.running_mean.data_ptr(),
+                         bn.running_var.data_ptr(), scale.data_ptr(), shift.data_ptr())
+            else:
+                self._setup_op("bpb_bn_eval_fold", bn.weight.data_ptr(), bn.bias.data_ptr(),
+                               bn.running_mean.data_ptr(), bn.running_var.data_ptr(), BN_EPS, y.c - c_lo,
+                               scale[c_lo:].data_ptr(), shift[c_lo:].data_ptr())
         return Lazy(y, scale, shift)
 
     def apply(self, lz: Lazy, relu, res=None) -> Act:
@@ -253,23 +288,14 @@ class ForwardPlan:
 
     def ibn_relu(self, x: Act, conv, ibn) -> Act:
         """conv -> IBN (InstanceNorm first half | BatchNorm second half) -> ReLU (resnet_fastreid.py:108-122,224-226)."""
-        raw, stats, tiles = self.conv_raw(x, conv)
-        c, half = raw.c, ibn.half
-        bn = ibn.BN
-        scale, shift = self._small((c,)), self._small((c,))
-        if self.training:
-            mom = bn.momentum if bn.momentum is not None else 0.1
-            self._op("bpb_bn_finalize", stats.data_ptr(), tiles, c, half, raw.m, bn.weight.data_ptr(),
-                     bn.bias.data_ptr(), BN_EPS, float(mom), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
-                     scale.data_ptr(), shift.data_ptr())
-        else:
-            self._op("bpb_bn_eval_fold", bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
-                     bn.running_var.data_ptr(), BN_EPS, c - half, scale[half:].data_ptr(), shift[half:].data_ptr())
+        half = ibn.half
+        lz = self.conv_bn(x, conv, ibn.BN, c_lo=half)
+        raw, c = lz.raw, lz.raw.c
         mr = self._small((raw.n, half, 2))
         self._op("bpb_instnorm_stats", raw.t.data_ptr(), mr.data_ptr(), raw.n, raw.h * raw.w, c, 0, half, BN_EPS)
         y = self._act(raw.n, raw.h, raw.w, c)
         self._op("bpb_ibn_apply", raw.t.data_ptr(), mr.data_ptr(), ibn.IN.weight.data_ptr(), ibn.IN.bias.data_ptr(),
-                 scale.data_ptr(), shift.data_ptr(), y.t.data_ptr(), raw.n, raw.h * raw.w, c, half, 1)
+                 lz.scale.data_ptr(), lz.shift.data_ptr(), y.t.data_ptr(), raw.n, raw.h * raw.w, c, half, 1)
         return y
 
     def fuse(self, terms, out_like: Act, relu=True) -> Act:
@@ -484,7 +510,18 @@ class ForwardPlan:
             raise KeyError(f"unknown backbone container {type(bb)}")
         self.build_head(feats)
 
+    def _run_list(self, ops):
+        stream = torch.cuda.current_stream().cuda_stream
+        err = self.lib.bpb_last_error
+        for fn, args, name in ops:
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise RuntimeError(f"{name} failed (rc={rc}): {err().decode()}")
+
     def _launch_all(self):
+        if self._need_setup:
+            self._run_list(self.setup_ops)
+            self._need_setup = False
         stream = torch.cuda.current_stream().cuda_stream
         err = self.lib.bpb_last_error
         for fn, args, name in self.ops:
@@ -494,6 +531,9 @@ class ForwardPlan:
 
     def run(self, images):
         self.images.copy_(images, non_blocking=True)
+        if self._need_setup:
+            self._run_list(self.setup_ops)
+            self._need_setup = False
         if self.use_graph:
             if self.graph is None:
                 # warm-up outside capture (first-call attribute setup), then capture

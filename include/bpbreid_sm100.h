@@ -32,6 +32,16 @@ int bpb_abi_version(void);
 int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                   int ksize, int stride, int bn_hint, void* stream);
 int bpb_conv_num_mtiles(int n, int ho, int wo);
+/* Same convolution with the train-mode BatchNorm that follows it fused into the launch (conv + nn.BatchNorm2d call
+ * pairs, e.g. hrnet.py:82-83): every CTA adds its per-channel sums to `bn_workspace` (fp64 atomics) and the last CTA
+ * turns them into scale/shift [cout] (biased batch variance), updates running_mean/var like nn.BatchNorm2d and
+ * leaves the workspace zeroed.  bn_workspace: bpb_conv_bn_workspace_bytes(cout) bytes, zero-initialised ONCE by the
+ * caller.  gamma/beta/running_* cover channels [c_lo, cout).  `stats` (per-tile partials) is optional. */
+int bpb_conv_bn_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
+                     int ksize, int stride, int bn_hint, void* bn_workspace, const float* gamma, const float* beta,
+                     float eps, float momentum, float* running_mean, float* running_var, int c_lo, float* scale,
+                     float* shift, void* stream);
+int64_t bpb_conv_bn_workspace_bytes(int cout);
 /* SIMT reference convolution, same operands (validation / shapes the tensor-core tiler rejects). */
 int bpb_conv_ref_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize,
                       int stride, void* stream);
