@@ -224,6 +224,7 @@ def run_gpu_arm(args, rank, world):
                                use_gpu=True, config=make_cfg()).to(dev)
     model.train()
     model.use_cuda_graph = not args.no_graph
+    model.materialize_spatial_features = False      # the 1920-ch map is an unused *output* of forward+loss
     crit = losses.GiLtLoss(None, use_visibility_scores=False, triplet_margin=0.3, use_gpu=True)
     n = PER_GPU_BATCH
     images_h, pids_h = synth_batch(n, 1 + rank)
@@ -252,6 +253,13 @@ def run_gpu_arm(args, rank, world):
         step_device()
     barrier()
     plan = next(iter(model._plans.values()))
+    if args.profile:
+        torch.cuda.profiler.start()
+        step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile": "one step", "launches": sum(KERNELS_PER_CALL.get(n_, 1) for _, _, n_ in plan.ops)}))
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -298,7 +306,9 @@ def run_gpu_arm(args, rank, world):
                    "per_gpu_batch": n, "global_batch": n * world,
                    "parallelism": f"dp{world}: batch sharded, embeddings all-gathered for global-batch mining",
                    "l2": "working set >> 126 MB L2 and a 256 MB flush buffer is written between timed iterations",
-                   "cuda_graph": bool(model.use_cuda_graph), "loss": loss_val},
+                   "cuda_graph": bool(model.use_cuda_graph), "loss": loss_val,
+                   "head": "evaluated on the 4 un-concatenated HRNet branch maps (linear identity); the [N,1920,64,32] "
+                           "concat, which forward+loss never consumes, is not written"},
         "clocks": clocks,
         "e2e": {"value": world * n * args.steps / e2e_s, "unit": "images/s",
                 "h2d_bytes_per_step": int(images_pin.numel() * 4), "d2h_bytes_per_step": 4},
@@ -323,6 +333,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="run ONE forward+loss step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -39,6 +39,10 @@ _SIGS = {
     "bpb_part_pool": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "bpb_linear_tf32": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bpb_bn1d": [_P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P],
+    "bpb_head_branch_stats": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P],
+    "bpb_head_lowres_logits": [_P, _P, _L, _I, _I, _I, _I, _P, _P],
+    "bpb_head_pixel": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "bpb_head_branch_pool": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "bpb_vis_unpack": [_P, _P, _I, _I, _P, _P, _P],
     "bpb_weighted_sum": [_P, _P, _I, _P, _P],
     "bpb_triplet_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P],

@@ -159,6 +159,24 @@ int bpb_bn1d(const float* x, const float* gamma, const float* beta, float eps, f
     return bn1d_train(x, gamma, beta, eps, momentum, running_mean, running_var, y, m, c, relu, training, S(stream));
 }
 
+int bpb_head_branch_stats(const void* x, int n, int hb, int wb, int cb, int h, int w, float* partial, int c_off,
+                          int ctot, void* stream) {
+    return head_branch_stats(x, n, hb, wb, cb, h, w, partial, c_off, ctot, S(stream));
+}
+int bpb_head_lowres_logits(const void* x, const float* wf, int64_t rows, int cb, int c_off, int ctot, int kp1,
+                           float* out, void* stream) {
+    return head_lowres_logits(x, wf, rows, cb, c_off, ctot, kp1, out, S(stream));
+}
+int bpb_head_pixel(const float* const* lowres_logits, float* const* mask_t, const int* hb, const int* wb, int nb,
+                   const float* bf, int n, int h, int w, int kp1, float* logits, float* probs, float* fg_mask,
+                   int* vis_bits, float* vis_cont, float* mask_sum, void* stream) {
+    return head_pixel(lowres_logits, mask_t, hb, wb, nb, bf, n, h, w, kp1, logits, probs, fg_mask, vis_bits, vis_cont,
+                      mask_sum, S(stream));
+}
+int bpb_head_branch_pool(const void* x, const float* mt, const float* mask_sum, int n, int q, int cb, int c_off,
+                         int ctot, int kp1, int hw_full, float* pooled, void* stream) {
+    return head_branch_pool(x, mt, mask_sum, n, q, cb, c_off, ctot, kp1, hw_full, pooled, S(stream));
+}
 int bpb_vis_unpack(const int* vis_bits, const float* vis_cont, int n, int kp1, uint8_t* out_b, float* out_f,
                    void* stream) {
     return vis_unpack(vis_bits, vis_cont, n, kp1, out_b, out_f, S(stream));

@@ -61,6 +61,17 @@ int bn1d_train(const float* x, const float* gamma, const float* beta, float eps,
 int vis_unpack(const int* vis_bits, const float* vis_cont, int n, int kp1, uint8_t* out_b, float* out_f,
                cudaStream_t stream);
 
+// ---- head_lowres.cu ---------------------------------------------------------------------------
+int head_branch_stats(const void* x, int n, int hb, int wb, int cb, int h, int w, float* partial, int c_off, int ctot,
+                      cudaStream_t stream);
+int head_lowres_logits(const void* x, const float* wf, int64_t rows, int cb, int c_off, int ctot, int kp1, float* out,
+                       cudaStream_t stream);
+int head_pixel(const float* const* lowres_logits, float* const* mask_t, const int* hb, const int* wb, int nb,
+               const float* bf, int n, int h, int w, int kp1, float* logits, float* probs, float* fg_mask,
+               int* vis_bits, float* vis_cont, float* mask_sum, cudaStream_t stream);
+int head_branch_pool(const void* x, const float* mt, const float* mask_sum, int n, int q, int cb, int c_off, int ctot,
+                     int kp1, int hw_full, float* pooled, cudaStream_t stream);
+
 // ---- loss.cu ----------------------------------------------------------------------------------
 int triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
                 float margin, float* dist_nn, float* hp, float* hn, int* hp_idx, int* hn_idx, float* out4,

@@ -250,49 +250,59 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     return o;
 }
 
+// Thread layout: tx = channel vector (8 channels) -- fixed per thread, so scale/shift live in registers and the row
+// loop has no division; ty = row lane.  Warps read/write contiguous 16-byte vectors of consecutive rows.
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, const uint4* __restrict__ res,
                                                        const float* __restrict__ rscale,
                                                        const float* __restrict__ rshift, uint4* __restrict__ y,
-                                                       int64_t nvec, int cvec, int relu) {
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % cvec) * 8;
-        float f[8], r[8];
-        unpack8(x[i], f);
-        const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(shift + c0), b1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                                                       int m, int cvec, int relu) {
+    const int width = cvec < 256 ? cvec : 256;
+    const int rows_per_block = 256 / width;
+    const int tx = threadIdx.x % width, ty = threadIdx.x / width;
+    if (ty >= rows_per_block) return;
+    for (int cv = tx; cv < cvec; cv += width) {
+        float sc[8], sh[8], rs[8], rb[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
-        if (res != nullptr) {
-            unpack8(res[i], r);
-            if (rscale != nullptr) {
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = scale[cv * 8 + j];
+            sh[j] = shift[cv * 8 + j];
+            rs[j] = rscale ? rscale[cv * 8 + j] : 1.f;
+            rb[j] = rshift ? rshift[cv * 8 + j] : 0.f;
+        }
+        for (int r = blockIdx.x * rows_per_block + ty; r < m; r += gridDim.x * rows_per_block) {
+            const size_t i = static_cast<size_t>(r) * cvec + cv;
+            float f[8];
+            unpack8(x[i], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += r[j] * rscale[c0 + j] + rshift[c0 + j];
-            } else {
+            for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
+            if (res != nullptr) {
+                float rr[8];
+                unpack8(res[i], rr);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += r[j];
+                for (int j = 0; j < 8; ++j) f[j] += rr[j] * rs[j] + rb[j];
             }
-        }
-        if (relu) {
+            if (relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            y[i] = pack8(f);
         }
-        y[i] = pack8(f);
     }
 }
 
 int bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* res_scale,
              const float* res_shift, void* y, int64_t m, int c, int relu, cudaStream_t stream) {
     BPB_CHECK(c % 8 == 0, "bn_apply: C=%d must be a multiple of 8", c);
-    const int64_t nvec = m * (c / 8);
-    int blocks = ceil_div(nvec, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    BPB_CHECK(m < (1ll << 31), "bn_apply: too many rows");
+    const int cvec = c / 8;
+    const int width = cvec < 256 ? cvec : 256;
+    const int rows_per_block = 256 / width;
+    int blocks = ceil_div(m, rows_per_block);
+    if (blocks > 148 * 8) blocks = 148 * 8;
     bn_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), scale, shift,
                                                 reinterpret_cast<const uint4*>(res), res_scale, res_shift,
-                                                reinterpret_cast<uint4*>(y), nvec, c / 8, relu);
+                                                reinterpret_cast<uint4*>(y), static_cast<int>(m), cvec, relu);
     BPB_LAUNCH_CHECK("bn_apply_kernel");
     return 0;
 }
@@ -311,37 +321,41 @@ struct FuseArgs {
 
 __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a, uint4* __restrict__ y, int n, int h, int wd, int cvec,
                                                        int relu) {
-    const int64_t total = static_cast<int64_t>(n) * h * wd * cvec;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int cv = i % cvec;
-        const int64_t pix = i / cvec;
-        const int ox = pix % wd, oy = (pix / wd) % h, im = pix / (static_cast<int64_t>(wd) * h);
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int width = cvec < 256 ? cvec : 256;
+    const int rows_per_block = 256 / width;
+    const int tx = threadIdx.x % width, ty = threadIdx.x / width;
+    if (ty >= rows_per_block) return;
+    const unsigned m = static_cast<unsigned>(n) * h * wd;
+    for (int cv = tx; cv < cvec; cv += width) {
+        for (unsigned r = blockIdx.x * rows_per_block + ty; r < m; r += gridDim.x * rows_per_block) {
+            const unsigned ox = r % wd, t = r / wd;
+            const unsigned oy = t % h, im = t / h;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j < a.nsrc) {
-                const int sh = a.sh[j];
-                const int hs = h >> sh, ws = wd >> sh;
-                const int64_t sidx = ((static_cast<int64_t>(im) * hs + (oy >> sh)) * ws + (ox >> sh)) * cvec + cv;
-                float f[8];
-                unpack8(a.src[j][sidx], f);
-                if (a.scale[j] != nullptr) {
-                    const float* sc = a.scale[j] + cv * 8;
-                    const float* sf = a.shift[j] + cv * 8;
+            for (int j = 0; j < 4; ++j) {
+                if (j < a.nsrc) {
+                    const int sh = a.sh[j];
+                    const unsigned hs = h >> sh, ws = wd >> sh;
+                    const size_t sidx = (static_cast<size_t>(im * hs + (oy >> sh)) * ws + (ox >> sh)) * cvec + cv;
+                    float f[8];
+                    unpack8(a.src[j][sidx], f);
+                    if (a.scale[j] != nullptr) {
+                        const float* sc = a.scale[j] + cv * 8;
+                        const float* sf = a.shift[j] + cv * 8;
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) acc[t] += f[t] * sc[t] + sf[t];
-                } else {
+                        for (int q = 0; q < 8; ++q) acc[q] += f[q] * sc[q] + sf[q];
+                    } else {
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) acc[t] += f[t];
+                        for (int q = 0; q < 8; ++q) acc[q] += f[q];
+                    }
                 }
             }
-        }
-        if (relu) {
+            if (relu) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) acc[t] = fmaxf(acc[t], 0.f);
+                for (int q = 0; q < 8; ++q) acc[q] = fmaxf(acc[q], 0.f);
+            }
+            y[static_cast<size_t>(r) * cvec + cv] = pack8(acc);
         }
-        y[i] = pack8(acc);
     }
 }
 
@@ -358,10 +372,11 @@ int fuse_sum(const void* const* srcs, const float* const* scales, const float* c
         a.sh[j] = shifts_log2[j];
         BPB_CHECK((h % (1 << a.sh[j])) == 0 && (wd % (1 << a.sh[j])) == 0, "fuse_sum: bad upsample factor");
     }
-    const int64_t total = static_cast<int64_t>(n) * h * wd * (c / 8);
-    int blocks = ceil_div(total, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    fuse_sum_kernel<<<blocks, 256, 0, stream>>>(a, reinterpret_cast<uint4*>(y), n, h, wd, c / 8, relu);
+    const int cvec = c / 8;
+    const int rows_per_block = 256 / (cvec < 256 ? cvec : 256);
+    int blocks = ceil_div(static_cast<int64_t>(n) * h * wd, rows_per_block);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    fuse_sum_kernel<<<blocks, 256, 0, stream>>>(a, reinterpret_cast<uint4*>(y), n, h, wd, cvec, relu);
     BPB_LAUNCH_CHECK("fuse_sum_kernel");
     return 0;
 }

@@ -31,6 +31,7 @@ struct GemmParams {
     int stages;
     int mode;       // 0: conv (4-D A map)   1: matrix (2-D A map)   2: part-concat matrix (3-D A map [parts, M, D])
     int dchunks;    // mode 2: K chunks per part
+    int kwrap;      // elements after which the A channel coordinate wraps (cin for conv, K for matrix, D for parts)
     int ksize, stride, pad, Ho, Wo;
     int ldo;        // output leading dimension (elements)
     void* out;
@@ -104,50 +105,56 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
-            uint32_t g = 0;                                     // global k-iteration counter (ring position)
+            // NOTE: this loop runs on ONE thread and paces the whole CTA: no integer division / modulo inside
+            // (measured: with `g % stages`, `it / kchunks` ... an iteration cost ~1450 cycles and the ring never filled)
+            int s = 0;
+            uint32_t ph = 0;                                    // parity of the ring round
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int m_tile = t / n_tiles, n_tile = t % n_tiles;
-                int n0 = 0, h0 = 0;
+                const int m_tile = t / n_tiles, n_tile = t - m_tile * n_tiles;
+                int n0 = 0, hbase = 0;
                 if (p.mode == 0) {
                     const int hw = p.Ho * p.Wo;
                     const int p0 = m_tile * kTileM;
                     n0 = p0 / hw;
-                    h0 = (p0 % hw) / p.Wo;
+                    hbase = ((p0 - n0 * hw) / p.Wo) * p.stride - p.pad;
                 }
-                for (int it = 0; it < p.k_iters; ++it, ++g) {
-                    const int s = g % p.stages;
-                    const uint32_t round = g / p.stages;
-                    mbar_wait(&empty_bar[s], (round & 1) ^ 1);
+                const int m0 = m_tile * kTileM, nb0 = n_tile * BN;
+                int tap_r = 0, tap_s = 0, kc = 0, bk = 0, part = 0;
+                for (int it = 0; it < p.k_iters; ++it) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * stage_bytes;
-                    uint8_t* b_dst = a_dst + a_bytes;
                     mbar_expect_tx(&full_bar[s], stage_bytes);
-                    const int tap = it / p.kchunks, kcidx = it % p.kchunks;
                     if (p.mode == 0) {
-                        const int r = tap / p.ksize, sx = tap % p.ksize;
-                        tma_load_4d(a_dst, &tmA, &full_bar[s], kcidx * p.kc, sx - p.pad, h0 * p.stride + r - p.pad, n0);
+                        tma_load_4d(a_dst, &tmA, &full_bar[s], kc, tap_s - p.pad, hbase + tap_r, n0);
                     } else if (p.mode == 1) {
-                        tma_load_2d(a_dst, &tmA, &full_bar[s], kcidx * p.kc, m_tile * kTileM);
+                        tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0);
                     } else {
-                        tma_load_3d(a_dst, &tmA, &full_bar[s], (kcidx % p.dchunks) * p.kc, m_tile * kTileM,
-                                    kcidx / p.dchunks);
+                        tma_load_3d(a_dst, &tmA, &full_bar[s], kc, m0, part);
                     }
-                    tma_load_2d(b_dst, &tmB, &full_bar[s], tap * p.cin + kcidx * p.kc, n_tile * BN);
+                    tma_load_2d(a_dst + a_bytes, &tmB, &full_bar[s], bk, nb0);
+                    bk += p.kc;                                 // B columns advance contiguously: tap*cin + kc
+                    kc += p.kc;
+                    if (kc == p.kwrap) {                        // end of the channel chunks of this tap / part
+                        kc = 0;
+                        ++part;
+                        if (++tap_s == p.ksize) { tap_s = 0; ++tap_r; }
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
         constexpr uint32_t idesc = make_idesc(kTf32, kTileM, BN);
-        const int instrs = p.row_bytes / 32;                   // 32 bytes of K per instruction (16 bf16 / 8 tf32)
-        uint32_t g = 0, lt = 0;
+        const int instrs = p.row_bytes >> 5;                   // 32 bytes of K per instruction (16 bf16 / 8 tf32)
+        int s = 0;
+        uint32_t ph = 0, lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const uint32_t buf = lt & 1, use = lt >> 1;
             mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
             tc_fence_after();
-            for (int it = 0; it < p.k_iters; ++it, ++g) {
-                const int s = g % p.stages;
-                const uint32_t round = g / p.stages;
-                mbar_wait(&full_bar[s], round & 1);
+            for (int it = 0; it < p.k_iters; ++it) {
+                mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -159,6 +166,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                     if (it == p.k_iters - 1) umma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
     } else {
@@ -340,8 +348,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     const int total = ((p.M + kTileM - 1) / kTileM) * ((p.N + BN - 1) / BN);
     // persistent: exactly as many CTAs as are co-resident (registers / smem via the occupancy API, TMEM: 2*BN
     // columns each) -- a static tile assignment must never have a second wave of CTAs
-    int per_sm = 1;
-    BPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNumThreads, smem));
+    // (shared memory is the binding limit: 56 registers x 192 threads allow 6 CTAs; the occupancy API under-reports
+    //  here, so the bound is computed directly: 227 KB usable per SM, ~4 KB static + reserved per CTA)
+    int per_sm = static_cast<int>((227 * 1024) / (smem + 4 * 1024));
     if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
@@ -400,6 +409,7 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     p.cin = cin;
     p.row_bytes = kc * 2;
     p.mode = 0;
+    p.kwrap = cin;
     p.ksize = ksize; p.stride = stride; p.pad = pad; p.Ho = ho; p.Wo = wo;
     p.ldo = cout;
     p.out = y;
@@ -458,6 +468,7 @@ int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bia
     p.M = m; p.N = n;
     p.kc = 32; p.kchunks = k / 32; p.k_iters = p.kchunks; p.cin = k;
     p.row_bytes = 128;
+    p.kwrap = k;
     p.mode = a_mode == 0 ? 1 : 2; p.ksize = 1; p.stride = 1; p.pad = 0; p.Ho = 0; p.Wo = 0;
     p.dchunks = 1;
     p.ldo = ldo; p.out = out; p.stats = nullptr; p.bias = bias;
@@ -478,6 +489,7 @@ int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bia
         BPB_CHECK(a_parts > 0 && k % a_parts == 0 && (k / a_parts) % 32 == 0, "linear_tf32_tc: bad part split");
         const int dd = k / a_parts;
         p.dchunks = dd / 32;
+        p.kwrap = dd;
         uint64_t dims[3] = {(uint64_t)dd, (uint64_t)m, (uint64_t)a_parts};
         uint64_t strides[2] = {(uint64_t)dd * 4, (uint64_t)m * dd * 4};
         uint32_t box[3] = {32, 128, 1};

@@ -73,6 +73,11 @@ class BPBreID(nn.Module):
         self.conv_impl = "tc"
         self.use_cuda_graph = False
         self.debug_trace = False
+        # HRNet only: evaluate the head on the un-concatenated branch maps (exact linear-algebra identity, see
+        # csrc/head_lowres.cu).  `materialize_spatial_features=False` additionally skips writing the [N,1920,H/4,W/4]
+        # map that is then only an *output* (5th element of the forward tuple becomes None).
+        self.lowres_head = True
+        self.materialize_spatial_features = True
 
     # -- forward ---------------------------------------------------------------------------------------------
     def plan_for(self, images):
@@ -80,7 +85,8 @@ class BPBreID(nn.Module):
             raise RuntimeError("bpbreid_b200.BPBreID runs on sm_100a only: move the model and the images to a CUDA "
                                "device (there is no CPU fallback path)")
         n, _, h, w = images.shape
-        key = (n, h, w, self.training, images.device.index, self.conv_impl, self.use_cuda_graph, self.debug_trace)
+        key = (n, h, w, self.training, images.device.index, self.conv_impl, self.use_cuda_graph, self.debug_trace,
+               self.lowres_head, self.materialize_spatial_features)
         plan = self._plans.get(key)
         if plan is None:
             from .plan import ForwardPlan

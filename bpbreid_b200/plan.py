@@ -383,11 +383,16 @@ class ForwardPlan:
             for mod in bb.stage4:
                 xs = self.hr_module(xs, mod)
             br = [self.bottleneck(xs[i], bb.incre_modules[i][0]) for i in range(4)]
-            feats = self._act(self.n, br[0].h, br[0].w, sum(b.c for b in br))
-            self._op("bpb_upsample_concat", self._ptr_array([b.t for b in br]), self._int_array([b.c for b in br]),
-                     self._int_array([b.h for b in br]), self._int_array([b.w for b in br]), 4, feats.t.data_ptr(),
-                     self.n, feats.h, feats.w)
-            keep.append(feats)
+            keep.extend(br)
+        return br
+
+    def hrnet_concat(self, br) -> Act:
+        """bilinear(align_corners) upsample + concat (hrnet.py:568-573): only needed when the caller wants the
+        `spatial_features` element of the 6-tuple or the map-based head."""
+        feats = self._act(self.n, br[0].h, br[0].w, sum(b.c for b in br))
+        self._op("bpb_upsample_concat", self._ptr_array([b.t for b in br]), self._int_array([b.c for b in br]),
+                 self._int_array([b.h for b in br]), self._int_array([b.w for b in br]), 4, feats.t.data_ptr(),
+                 self.n, feats.h, feats.w)
         self._trace("upcat", [], br, [feats])
         return feats
 
@@ -413,39 +418,96 @@ class ForwardPlan:
         return x
 
     # ------------------------------------------------------------------ head
-    def build_head(self, feats: Act):
-        m, K, n = self.model, self.K, self.n
-        kp1, J = K + 1, K + 3
+    def _alloc_head_outputs(self, h, w, c):
+        n, kp1, J = self.n, self.K + 1, self.K + 3
+        self.logits = self._small((n, kp1, h, w))
+        self.probs = self._small((n, kp1, h, w))
+        self.fg_mask = self._small((n, h, w))
+        self.vis_bits = self._small((n,), torch.int32)
+        self.vis_cont = self._small((n, kp1))
+        self.vis_b = self._small((n, kp1 + 1), torch.uint8)
+        self.vis_f = self._small((n, kp1 + 1))
+        self.pooled = self._small((J, n, c))
+
+    def build_head_front_map(self, feats: Act):
+        """Pixel classifier / masks / pooling on a materialised feature map (ResNet backbones, or HRNet with
+        lowres_head disabled)."""
+        m, n = self.model, self.n
+        kp1 = self.K + 1
         hw, c = feats.h * feats.w, feats.c
-        D = m.dim_reduce_output
-        ncls = m.num_classes
-        ld = (ncls + 3) // 4 * 4
-        self.feats = feats
         pc = m.pixel_classifier
-        # pixel classifier: BN2d statistics over the map, folded into the 1x1 conv
         if self.training:
             stats, tiles = self.colstats(Act(feats.t, n, feats.h, feats.w, c))
         else:
             stats, tiles = None, 0
         scale, shift = self.bn_scale_shift(stats, tiles, c, n * hw, pc.bn)
         wf, bf = self._small((kp1, c)), self._small((kp1,))
-        self._op("bpb_pixel_fold", pc.classifier.weight.data_ptr(), pc.classifier.bias.data_ptr(), scale.data_ptr(),
-                 shift.data_ptr(), kp1, c, wf.data_ptr(), bf.data_ptr())
-        self.logits = self._small((n, kp1, feats.h, feats.w))
-        self.probs = self._small((n, kp1, feats.h, feats.w))
-        self.fg_mask = self._small((n, feats.h, feats.w))
-        self.vis_bits = self._small((n,), torch.int32)
-        self.vis_cont = self._small((n, kp1))
+        fold = self._op if self.training else self._setup_op
+        fold("bpb_pixel_fold", pc.classifier.weight.data_ptr(), pc.classifier.bias.data_ptr(), scale.data_ptr(),
+             shift.data_ptr(), kp1, c, wf.data_ptr(), bf.data_ptr())
+        self._alloc_head_outputs(feats.h, feats.w, c)
         self._op("bpb_pixel_classify", feats.t.data_ptr(), wf.data_ptr(), bf.data_ptr(), n, hw, c, kp1,
                  self.logits.data_ptr(), self.probs.data_ptr(), self.fg_mask.data_ptr(), self.vis_bits.data_ptr(),
                  self.vis_cont.data_ptr())
-        self.vis_b = self._small((n, kp1 + 1), torch.uint8)
-        self.vis_f = self._small((n, kp1 + 1))
         self._op("bpb_vis_unpack", self.vis_bits.data_ptr(), self.vis_cont.data_ptr(), n, kp1, self.vis_b.data_ptr(),
                  self.vis_f.data_ptr())
-        self.pooled = self._small((J, n, c))
         self._op("bpb_part_pool", feats.t.data_ptr(), self.probs.data_ptr(), self.fg_mask.data_ptr(), n, hw, c, kp1,
                  self.pooled.data_ptr())
+
+    def build_head_front_branches(self, br):
+        """HRNet: the same head evaluated on the four un-concatenated branch maps (csrc/head_lowres.cu): bilinear
+        upsampling, the 1x1 classifier and the pooling sums are linear, so nothing at 1920 channels x stride 4 is
+        ever written.  BN2d batch statistics of the virtual upsampled map are accumulated on the fly."""
+        m, n = self.model, self.n
+        kp1, J = self.K + 1, self.K + 3
+        h, w = br[0].h, br[0].w
+        ctot = sum(b.c for b in br)
+        offs = [sum(b.c for b in br[:i]) for i in range(len(br))]
+        pc = m.pixel_classifier
+        scale, shift = self._small((ctot,)), self._small((ctot,))
+        if self.training:
+            partial = self._small((n, 2, ctot))
+            for b, off in zip(br, offs):
+                self._op("bpb_head_branch_stats", b.t.data_ptr(), n, b.h, b.w, b.c, h, w, partial.data_ptr(), off, ctot)
+            bn = pc.bn
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            self._op("bpb_bn_finalize", partial.data_ptr(), n, ctot, 0, n * h * w, bn.weight.data_ptr(),
+                     bn.bias.data_ptr(), BN_EPS, float(mom), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                     scale.data_ptr(), shift.data_ptr())
+        else:
+            self._setup_op("bpb_bn_eval_fold", pc.bn.weight.data_ptr(), pc.bn.bias.data_ptr(),
+                           pc.bn.running_mean.data_ptr(), pc.bn.running_var.data_ptr(), BN_EPS, ctot,
+                           scale.data_ptr(), shift.data_ptr())
+        wf, bf = self._small((kp1, ctot)), self._small((kp1,))
+        fold = self._op if self.training else self._setup_op
+        fold("bpb_pixel_fold", pc.classifier.weight.data_ptr(), pc.classifier.bias.data_ptr(), scale.data_ptr(),
+             shift.data_ptr(), kp1, ctot, wf.data_ptr(), bf.data_ptr())
+        self._alloc_head_outputs(h, w, ctot)
+        lows, mts = [], []
+        for b, off in zip(br, offs):
+            lo = self._small((n * b.h * b.w, kp1))
+            self._op("bpb_head_lowres_logits", b.t.data_ptr(), wf.data_ptr(), n * b.h * b.w, b.c, off, ctot, kp1,
+                     lo.data_ptr())
+            lows.append(lo)
+            mts.append(self._small((n, J, b.h * b.w)))
+        self.mask_sum = self._small((n, J))
+        self._op("bpb_head_pixel", self._ptr_array(lows), self._ptr_array(mts), self._int_array([b.h for b in br]),
+                 self._int_array([b.w for b in br]), len(br), bf.data_ptr(), n, h, w, kp1, self.logits.data_ptr(),
+                 self.probs.data_ptr(), self.fg_mask.data_ptr(), self.vis_bits.data_ptr(), self.vis_cont.data_ptr(),
+                 self.mask_sum.data_ptr())
+        self._op("bpb_vis_unpack", self.vis_bits.data_ptr(), self.vis_cont.data_ptr(), n, kp1, self.vis_b.data_ptr(),
+                 self.vis_f.data_ptr())
+        for b, off, mt in zip(br, offs, mts):
+            self._op("bpb_head_branch_pool", b.t.data_ptr(), mt.data_ptr(), self.mask_sum.data_ptr(), n, b.h * b.w, b.c,
+                     off, ctot, kp1, h * w, self.pooled.data_ptr())
+        return ctot
+
+    def build_head_back(self, c):
+        m, K, n = self.model, self.K, self.n
+        J = K + 3
+        D = m.dim_reduce_output
+        ncls = m.num_classes
+        ld = (ncls + 3) // 4 * 4
         # dim reduce: Linear(C->D) + BN1d + ReLU for {global, fg, bg, parts (K*N rows jointly)}
         lin = self._small((J * n, D))
         self.emb = self._small((J * n, D))
@@ -497,18 +559,31 @@ class ForwardPlan:
 
     # ------------------------------------------------------------------ build / run
     def _build(self):
+        self.feats = None
         bb = self.model.backbone_appearance_feature_extractor
         if not self.cfg.learnable_attention_enabled:
             raise NotImplementedError("external-mask attention (learnable_attention_enabled=False) is not built yet")
         if self.cfg.dim_reduce != "after_pooling" or self.cfg.pooling != "gwap" or self.cfg.normalization != "identity":
             raise NotImplementedError("only the shipped configuration (gwap / identity / after_pooling) is built")
+        lowres = getattr(self.model, "lowres_head", True)
+        want_map = getattr(self.model, "materialize_spatial_features", True)
         if isinstance(bb, P.HRNet32Params):
-            feats = self.build_hrnet(bb)
+            br = self.build_hrnet(bb)
+            if lowres:
+                c = self.build_head_front_branches(br)
+                if want_map:
+                    self.feats = self.hrnet_concat(br)
+            else:
+                self.feats = self.hrnet_concat(br)
+                self.build_head_front_map(self.feats)
+                c = self.feats.c
         elif isinstance(bb, P.ResNet50Params):
-            feats = self.build_resnet(bb)
+            self.feats = self.build_resnet(bb)
+            self.build_head_front_map(self.feats)
+            c = self.feats.c
         else:
             raise KeyError(f"unknown backbone container {type(bb)}")
-        self.build_head(feats)
+        self.build_head_back(c)
 
     def _run_list(self, ops):
         stream = torch.cuda.current_stream().cuda_stream
@@ -570,7 +645,7 @@ class ForwardPlan:
                   "conct": self.scores_conct[:, :ncls],
                   "parts": sc[3 * n:].view(K, n, self.ld).permute(1, 0, 2)[:, :, :ncls]}
         f = self.feats
-        spatial = f.t.view(n, f.h, f.w, f.c).permute(0, 3, 1, 2)
+        spatial = None if f is None else f.t.view(n, f.h, f.w, f.c).permute(0, 3, 1, 2)
         masks = {"globl": torch.ones_like(self.fg_mask), "backg": self.probs[:, 0], "foreg": self.fg_mask,
                  "conct": self.fg_mask, "parts": self.probs[:, 1:]}
         return embeddings, visibility, scores, self.logits, spatial, masks

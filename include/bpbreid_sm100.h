@@ -102,6 +102,25 @@ int bpb_linear_tf32(const float* a, int64_t lda, const float* w, const float* bi
 int bpb_bn1d(const float* x, const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
              float* running_var, float* y, int m, int c, int relu, int training, void* stream);
 
+/* ---- head on the UN-concatenated HRNet branch maps (linear algebra identity, csrc/head_lowres.cu): replaces the same
+ *      reference lines as the four entry points above plus hrnet.py:568-573, without materialising [N,1920,H/4,W/4] ---- */
+/* per-image partial BN2d statistics of the bilinearly-upsampled branch -> partial[n][2][ctot] at channel c_off
+ * (reduce with bpb_bn_finalize(tiles = n)). */
+int bpb_head_branch_stats(const void* x, int n, int hb, int wb, int cb, int h, int w, float* partial, int c_off,
+                          int ctot, void* stream);
+/* out[row][k] = sum_c wf[k][c_off+c] x[row][c] : the folded pixel classifier applied at the branch's own resolution. */
+int bpb_head_lowres_logits(const void* x, const float* wf, int64_t rows, int cb, int c_off, int ctot, int kp1,
+                           float* out, void* stream);
+/* full-resolution logits = bf + sum_b bilinear(lowres_logits[b]) -> softmax -> masks / visibility (same outputs as
+ * bpb_pixel_classify) + mask_sum[n][K+3] and the transposed-upsampled masks mask_t[b][n][K+3][hb*wb]
+ * (rows: global, foreground, background, parts). */
+int bpb_head_pixel(const float* const* lowres_logits, float* const* mask_t, const int* hb, const int* wb, int nb,
+                   const float* bf, int n, int h, int w, int kp1, float* logits, float* probs, float* fg_mask,
+                   int* vis_bits, float* vis_cont, float* mask_sum, void* stream);
+/* pooled[j][n][c_off+c] = norm_j * sum_q mask_t[n][j][q] x[n][q][c]  (same pooled layout as bpb_part_pool). */
+int bpb_head_branch_pool(const void* x, const float* mt, const float* mask_sum, int n, int q, int cb, int c_off,
+                         int ctot, int kp1, int hw_full, float* pooled, void* stream);
+
 /* Visibility scores (bpbreid.py:182-192): out_b / out_f [n, K+2] = {background, part_1..K, foreground}. */
 int bpb_vis_unpack(const int* vis_bits, const float* vis_cont, int n, int kp1, uint8_t* out_b, float* out_f,
                    void* stream);

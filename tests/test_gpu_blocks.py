@@ -86,7 +86,13 @@ def test_every_block_matches_bf16_oracle_on_its_own_input(name):
     print(name, "blocks checked:", checked, "worst rel err per kind:", {k: round(v, 5) for k, v in worst.items()})
     # ---- head, teacher-forced on the CUDA feature map (fp32 math on both sides; tf32 Linear layers) ----
     emb, vis, ids, pix, feats, masks = out
-    f32 = feats.float().cpu()
+    up = [e for e in plan.trace if e["kind"] == "upcat"]
+    if up:      # HRNet: the head consumes the branch maps directly (fp32 interpolation, nothing rounded to bf16)
+        br = [nchw(a) for a in up[0]["ins"]]
+        hh, ww = br[0].shape[2:]
+        f32 = torch.cat([br[0]] + [F.interpolate(b, size=(hh, ww), mode="bilinear", align_corners=True) for b in br[1:]], 1)
+    else:
+        f32 = feats.float().cpu()
     with torch.no_grad():
         o = MDL.bpbreid_head(MDL.Ctx(True, None), f32, sd, c["K"])
     np.testing.assert_allclose(pix.cpu().numpy(), o[3].numpy(), rtol=0, atol=2e-3 * float(o[3].abs().max()) + 1e-5)

@@ -21,7 +21,7 @@ def main(path, out=None):
         scale = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3}.get(unit, 1e-3)
         rows.append((r["Kernel Name"], v * scale))
     last = max((i for i, (k, _) in enumerate(rows) if "stem_conv" in k), default=0)
-    step = rows[last:]
+    step = rows[last:] if last > 0 else rows
     # cut the probe / e2e launches that follow the step: stop at the next stem conv (none) or at weighted_sum
     for i, (k, _) in enumerate(step):
         if "weighted_sum" in k:
