@@ -29,8 +29,11 @@ struct GemmParams {
     int cin;        // channels per tap (column offset of a tap inside B)
     int row_bytes;  // 128 or 64: TMA inner box bytes == swizzle span
     int stages;
-    int mode;       // 0: conv (4-D A map)   1: matrix (2-D A map)   2: part-concat matrix (3-D A map [parts, M, D])
+    int mode;       // 0: conv, one tap per stage   1: matrix (2-D A map)   2: part-concat matrix (3-D A map)
+                    // 3: 3x3 stride-1 conv, three vertical taps per stage (row shift)
     int dchunks;    // mode 2: K chunks per part
+    int a_rows;     // rows of the A stage: 128, or 128 + 2*Wo in mode 3
+    int rshift_bytes;   // mode 3: bytes between vertically adjacent taps inside the A stage (Wo * row_bytes)
     int kwrap;      // elements after which the A channel coordinate wraps (cin for conv, K for matrix, D for parts)
     int ksize, stride, pad, Ho, Wo;
     int ldo;        // output leading dimension (elements)
@@ -56,6 +59,12 @@ enum Epi { EPI_RAW_STATS = 0, EPI_F32_BIAS = 1 };
 // consecutive tiles share their A rows in L2).  The TMA producer runs ahead across tile boundaries through the smem
 // ring, the MMA warp alternates between two TMEM accumulators, and the epilogue warps drain one accumulator while the
 // next tile's MMAs are in flight.
+//
+// mode 3 ("row shift", 3x3 stride-1 convs whose 128-pixel tile lies inside one image): one TMA box of (rows+2) image
+// rows per horizontal tap s feeds the THREE vertical taps r = 0,1,2 -- tap r is the same shared-memory tile entered
+// r*Wo rows further down (a multiple of the 8-row swizzle atom, so the K-major descriptor just gets a new start
+// address).  A-operand traffic from L2 drops from 9 to 3*(rows+2)/rows tiles per output tile and every ring stage
+// carries three taps' worth of MMAs, which amortises the single-thread issue loop.
 template <int BN, bool kTf32, int kEpi>
 __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
@@ -64,9 +73,10 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_bytes = kTileM * p.row_bytes;
-    const int b_bytes = BN * p.row_bytes;
-    const int stage_bytes = a_bytes + b_bytes;
+    const int taps = p.mode == 3 ? 3 : 1;                      // taps (MMA groups) per ring stage
+    const int a_bytes = p.a_rows * p.row_bytes;
+    const int b_tap_bytes = BN * p.row_bytes;
+    const int stage_bytes = a_bytes + taps * b_tap_bytes;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int m_tiles = (p.M + kTileM - 1) / kTileM;
     const int total_tiles = m_tiles * n_tiles;
@@ -80,6 +90,11 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     __shared__ uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float red_smem[2][8][BN < 32 ? 32 : BN];        // [sum|sq][row group][col]
+
+    // shared-window addresses, computed once
+    const uint32_t smem_a = smem_u32(smem);
+    const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
+    const uint32_t accf_a = smem_u32(&acc_full[0]), acce_a = smem_u32(&acc_empty[0]);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -105,14 +120,15 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
-            // NOTE: this loop runs on ONE thread and paces the whole CTA: no integer division / modulo inside
-            // (measured: with `g % stages`, `it / kchunks` ... an iteration cost ~1450 cycles and the ring never filled)
+            // NOTE: this loop runs on ONE thread and paces the whole CTA: no integer division / modulo and no
+            // address-of-shared inside (measured: `g % stages`, `it / kchunks` made an iteration cost ~1450 cycles)
             int s = 0;
             uint32_t ph = 0;                                    // parity of the ring round
+            uint32_t stage_a = smem_a, fb = full_a, eb = empty_a;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int m_tile = t / n_tiles, n_tile = t - m_tile * n_tiles;
                 int n0 = 0, hbase = 0;
-                if (p.mode == 0) {
+                if (p.mode == 0 || p.mode == 3) {
                     const int hw = p.Ho * p.Wo;
                     const int p0 = m_tile * kTileM;
                     n0 = p0 / hw;
@@ -121,17 +137,24 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                 const int m0 = m_tile * kTileM, nb0 = n_tile * BN;
                 int tap_r = 0, tap_s = 0, kc = 0, bk = 0, part = 0;
                 for (int it = 0; it < p.k_iters; ++it) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* a_dst = smem + s * stage_bytes;
-                    mbar_expect_tx(&full_bar[s], stage_bytes);
-                    if (p.mode == 0) {
-                        tma_load_4d(a_dst, &tmA, &full_bar[s], kc, tap_s - p.pad, hbase + tap_r, n0);
-                    } else if (p.mode == 1) {
-                        tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0);
+                    mbar_wait_a(eb, ph ^ 1);
+                    mbar_expect_tx_a(fb, stage_bytes);
+                    if (p.mode == 3) {
+                        tma_load_4d_a(stage_a, &tmA, fb, kc, tap_s - 1, hbase, n0);
+                        const int col = tap_s * p.cin + kc;          // tap (r, s) lives at column (3 r + s) * cin + kc
+                        tma_load_2d_a(stage_a + a_bytes, &tmB, fb, col, nb0);
+                        tma_load_2d_a(stage_a + a_bytes + b_tap_bytes, &tmB, fb, col + 3 * p.cin, nb0);
+                        tma_load_2d_a(stage_a + a_bytes + 2 * b_tap_bytes, &tmB, fb, col + 6 * p.cin, nb0);
                     } else {
-                        tma_load_3d(a_dst, &tmA, &full_bar[s], kc, m0, part);
+                        if (p.mode == 0) {
+                            tma_load_4d_a(stage_a, &tmA, fb, kc, tap_s - p.pad, hbase + tap_r, n0);
+                        } else if (p.mode == 1) {
+                            tma_load_2d_a(stage_a, &tmA, fb, kc, m0);
+                        } else {
+                            tma_load_3d_a(stage_a, &tmA, fb, kc, m0, part);
+                        }
+                        tma_load_2d_a(stage_a + a_bytes, &tmB, fb, bk, nb0);
                     }
-                    tma_load_2d(a_dst + a_bytes, &tmB, &full_bar[s], bk, nb0);
                     bk += p.kc;                                 // B columns advance contiguously: tap*cin + kc
                     kc += p.kc;
                     if (kc == p.kwrap) {                        // end of the channel chunks of this tap / part
@@ -139,7 +162,8 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                         ++part;
                         if (++tap_s == p.ksize) { tap_s = 0; ++tap_r; }
                     }
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    stage_a += stage_bytes; fb += 8; eb += 8;
+                    if (++s == p.stages) { s = 0; ph ^= 1; stage_a = smem_a; fb = full_a; eb = empty_a; }
                 }
             }
         }
@@ -147,26 +171,33 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
         // ------------------------------ MMA issuer ------------------------------
         constexpr uint32_t idesc = make_idesc(kTf32, kTileM, BN);
         const int instrs = p.row_bytes >> 5;                   // 32 bytes of K per instruction (16 bf16 / 8 tf32)
+        const uint64_t desc_hi = make_kmajor_desc(0, p.row_bytes);          // everything but the start address
+        const uint32_t rshift16 = static_cast<uint32_t>(p.rshift_bytes) >> 4;
+        const uint32_t btap16 = static_cast<uint32_t>(b_tap_bytes) >> 4;
         int s = 0;
         uint32_t ph = 0, lt = 0;
+        uint32_t stage_a = smem_a, fb = full_a, eb = empty_a;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const uint32_t buf = lt & 1, use = lt >> 1;
-            mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+            mbar_wait_a(acce_a + buf * 8, (use & 1) ^ 1);
             tc_fence_after();
+            const uint32_t tacc = tmem_base + buf * BN;
             for (int it = 0; it < p.k_iters; ++it) {
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait_a(fb, ph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-                    const uint64_t da = make_kmajor_desc(a_addr, p.row_bytes);
-                    const uint64_t db = make_kmajor_desc(a_addr + a_bytes, p.row_bytes);
-                    for (int k = 0; k < instrs; ++k)
-                        umma<kTf32>(tmem_base + buf * BN, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&empty_bar[s]);                // smem slot free once these MMAs retire
-                    if (it == p.k_iters - 1) umma_commit(&acc_full[buf]);
+                    const uint64_t da = desc_hi | static_cast<uint64_t>((stage_a & 0x3FFFFu) >> 4);
+                    const uint64_t db = desc_hi | static_cast<uint64_t>(((stage_a + a_bytes) & 0x3FFFFu) >> 4);
+                    for (int r = 0; r < taps; ++r)
+                        for (int k = 0; k < instrs; ++k)
+                            umma<kTf32>(tacc, da + r * rshift16 + 2 * k, db + r * btap16 + 2 * k, idesc,
+                                        (it > 0 || r > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_a(eb);                          // smem slot free once these MMAs retire
+                    if (it == p.k_iters - 1) umma_commit_a(accf_a + buf * 8);
                 }
                 __syncwarp();
-                if (++s == p.stages) { s = 0; ph ^= 1; }
+                stage_a += stage_bytes; fb += 8; eb += 8;
+                if (++s == p.stages) { s = 0; ph ^= 1; stage_a = smem_a; fb = full_a; eb = empty_a; }
             }
         }
     } else {
@@ -180,7 +211,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
             const uint32_t buf = lt & 1, use = lt >> 1;
             const int m0 = m_tile * kTileM, c_base = n_tile * BN;
             const int valid_rows = min(kTileM, p.M - m0);
-            mbar_wait(&acc_full[buf], use & 1);
+            mbar_wait_a(accf_a + buf * 8, use & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
 
@@ -193,7 +224,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                     tmem_ld_wait();
                     if (c0 + 32 >= BN) {                        // accumulator fully read: hand it back to the MMA warp
                         tc_fence_before();
-                        mbar_arrive(&acc_empty[buf]);
+                        mbar_arrive_a(acce_a + buf * 8);
                     }
                     if (row < valid_rows) {
                         float* dst = out + static_cast<size_t>(m0 + row) * p.ldo + c_base + c0;
@@ -225,7 +256,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                     tmem_ld_wait();
                     if (c0 + 32 >= BN) {
                         tc_fence_before();
-                        mbar_arrive(&acc_empty[buf]);
+                        mbar_arrive_a(acce_a + buf * 8);
                     }
                     uint4* dst = reinterpret_cast<uint4*>(epi_tile + row * kPitch + c0 * 2);
 #pragma unroll
@@ -334,11 +365,12 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
 // ----------------------------------------------------------------------------------------------
 template <int BN, bool kTf32, int kEpi>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    const int stage_bytes = (kTileM + BN) * p.row_bytes;
+    const int stage_bytes = (p.a_rows + (p.mode == 3 ? 3 : 1) * BN) * p.row_bytes;
     const size_t epi = kEpi == EPI_RAW_STATS
                            ? static_cast<size_t>(kTileM) * (BN * 2 + 16) + (p.bn_acc ? 2 * sizeof(float) * p.N : 0)
                            : 0;
     const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + epi + 1024;
+    BPB_CHECK(smem <= 200 * 1024, "tc_gemm: %zu bytes of shared memory requested", smem);
     auto kern = tc_gemm_kernel<BN, kTf32, kEpi>;
     static bool configured = false;
     if (!configured) {
@@ -367,13 +399,11 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     return 0;
 }
 
-static int pick_stages(int bn, int row_bytes, int k_iters) {
-    // ring depth: ~64 KB of operands in flight per CTA (the ring spans tile boundaries in the persistent kernel)
-    const int stage_bytes = (kTileM + bn) * row_bytes;
-    int s = (64 * 1024) / stage_bytes;
+static int pick_stages(int stage_bytes, int budget_bytes) {
+    // ring depth: the ring spans tile boundaries in the persistent kernel, so depth only has to cover the TMA latency
+    int s = budget_bytes / stage_bytes;
     if (s > 8) s = 8;
-    if (s < 3) s = 3;
-    (void)k_iters;
+    if (s < 2) s = 2;
     return s;
 }
 
@@ -404,17 +434,22 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     p.M = n * ho * wo;
     p.N = cout;
     p.kchunks = cin / kc;
-    p.k_iters = ksize * ksize * p.kchunks;
     p.kc = kc;
     p.cin = cin;
     p.row_bytes = kc * 2;
-    p.mode = 0;
     p.kwrap = cin;
     p.ksize = ksize; p.stride = stride; p.pad = pad; p.Ho = ho; p.Wo = wo;
     p.ldo = cout;
     p.out = y;
     p.stats = stats;
     p.bias = nullptr;
+    // row-shift mode: 3x3 stride-1, tile inside one image, vertical tap offset = whole swizzle atoms (Wo % 8 == 0)
+    const bool rowshift = ksize == 3 && stride == 1 && bnimg == 1 && (wo % 8) == 0 && (bn_hint & 0x100) == 0;
+    bn_hint &= 0xFF;
+    p.mode = rowshift ? 3 : 0;
+    p.a_rows = rowshift ? kTileM + 2 * wo : kTileM;
+    p.rshift_bytes = rowshift ? wo * p.row_bytes : 0;
+    p.k_iters = rowshift ? 3 * p.kchunks : ksize * ksize * p.kchunks;
     if (bn != nullptr) {
         BPB_CHECK(bn->workspace != nullptr && bn->scale != nullptr && bn->shift != nullptr, "conv_bf16_tc: BN outputs");
         p.bn_acc = reinterpret_cast<double*>(bn->workspace);
@@ -428,15 +463,22 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
         p.c_lo = bn->c_lo;
     }
     const int m_tiles = (p.M + kTileM - 1) / kTileM;
-    const int bn_tile = pick_bn(m_tiles, cout, bn_hint);
-    p.stages = pick_stages(bn_tile, p.row_bytes, p.k_iters);
+    int bn_tile = pick_bn(m_tiles, cout, bn_hint);
+    if (rowshift && bn_tile > 64 && p.row_bytes == 128) bn_tile = 64;      // keep >= 3 ring stages in shared memory
+    {
+        const int stage_bytes = (p.a_rows + (rowshift ? 3 : 1) * bn_tile) * p.row_bytes;
+        const int epi_bytes = kTileM * (bn_tile * 2 + 16) + (bn ? 8 * cout : 0);
+        const int budget = !rowshift ? 72 * 1024 : (p.row_bytes == 64 ? 92 * 1024 : 150 * 1024 - epi_bytes);
+        p.stages = pick_stages(stage_bytes, budget);
+    }
 
     const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tmA, tmB;
     {
         uint64_t dims[4] = {(uint64_t)cin, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
         uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)wd * cin * 2, (uint64_t)h * wd * cin * 2};
-        uint32_t box[4] = {(uint32_t)kc, (uint32_t)(wo * stride), (uint32_t)(bh * stride), (uint32_t)bnimg};
+        uint32_t box[4] = {(uint32_t)kc, (uint32_t)(wo * stride), (uint32_t)((rowshift ? bh + 2 : bh) * stride),
+                           (uint32_t)bnimg};
         uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         if (make_tensor_map(&tmA, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box, es, sw)) return 4;
     }
@@ -469,13 +511,14 @@ int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bia
     p.kc = 32; p.kchunks = k / 32; p.k_iters = p.kchunks; p.cin = k;
     p.row_bytes = 128;
     p.kwrap = k;
+    p.a_rows = kTileM; p.rshift_bytes = 0;
     p.mode = a_mode == 0 ? 1 : 2; p.ksize = 1; p.stride = 1; p.pad = 0; p.Ho = 0; p.Wo = 0;
     p.dchunks = 1;
     p.ldo = ldo; p.out = out; p.stats = nullptr; p.bias = bias;
     const int m_tiles = (m + kTileM - 1) / kTileM;
     int bn = n >= 128 ? 128 : (n >= 64 ? 64 : 32);
     while (bn > 32 && m_tiles * ((n + bn - 1) / bn) < 148) bn >>= 1;
-    p.stages = pick_stages(bn, 128, p.k_iters);
+    p.stages = pick_stages((kTileM + bn) * 128, 72 * 1024);
     CUtensorMap tmA, tmB;
     if (a_mode == 0) {
         BPB_CHECK(lda % 4 == 0 && lda >= k, "linear_tf32_tc: lda=%lld invalid", (long long)lda);

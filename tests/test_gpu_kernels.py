@@ -80,6 +80,53 @@ def test_conv_tc_matches_fp32_reference(shape):
     assert rel_err(y2.float(), ref) < 1e-2
 
 
+@pytest.mark.parametrize("shape", [(4, 64, 32, 32, 32, 3, 1), (4, 32, 16, 64, 64, 3, 1), (4, 16, 8, 128, 128, 3, 1),
+                                   (2, 64, 32, 64, 64, 3, 1), (2, 64, 32, 256, 32, 3, 1)])
+def test_conv_rowshift_mode_equals_single_tap_mode(shape):
+    """3x3 stride-1 convs use the 'row shift' schedule (three vertical taps per TMA box); bn_hint bit 8 forces the
+    one-tap-per-stage schedule.  Both must produce the same bf16 outputs (same products, same fp32 accumulation
+    order up to tap grouping)."""
+    n, h, w, cin, cout, k, s = shape
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).to(DEV)
+    wp = pack_w((torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * 9)) ** 0.5)).to(DEV)
+    ya = torch.empty(n, h, w, cout, device=DEV, dtype=torch.bfloat16)
+    yb = torch.empty_like(ya)
+    _lib.call("bpb_conv_bf16", x.data_ptr(), wp.data_ptr(), ya.data_ptr(), None, n, h, w, cin, cout, k, s, 0, S())
+    _lib.call("bpb_conv_bf16", x.data_ptr(), wp.data_ptr(), yb.data_ptr(), None, n, h, w, cin, cout, k, s, 0x100, S())
+    torch.cuda.synchronize()
+    assert rel_err(ya.float(), yb.float()) < 4e-3          # one bf16 ulp where the fp32 sums round differently
+
+
+def test_conv_fused_bn_matches_two_pass_statistics():
+    """bpb_conv_bn_bf16 (last-CTA finalize) == conv + per-tile partials + bpb_bn_finalize, incl. running stats, and the
+    workspace is left zeroed so the same buffer can be reused by the next launch."""
+    n, h, w, cin, cout, k, s = 8, 32, 16, 64, 64, 3, 1
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).to(DEV)
+    wp = pack_w(torch.randn(cout, cin, k, k, generator=g) * 0.05).to(DEV)
+    gamma, beta = (torch.rand(cout, generator=g) + 0.5).to(DEV), torch.randn(cout, generator=g).to(DEV)
+    y1, y2 = (torch.empty(n, h, w, cout, device=DEV, dtype=torch.bfloat16) for _ in range(2))
+    ws = torch.zeros(_lib.query("bpb_conv_bn_workspace_bytes", cout), dtype=torch.uint8, device=DEV)
+    rm1, rv1, rm2, rv2 = (torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV),
+                          torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV))
+    sc1, sh1, sc2, sh2 = (torch.empty(cout, device=DEV) for _ in range(4))
+    for _ in range(2):      # twice: the second launch must find a clean workspace
+        rm1.zero_(); rv1.fill_(1.0)
+        _lib.call("bpb_conv_bn_bf16", x.data_ptr(), wp.data_ptr(), y1.data_ptr(), None, n, h, w, cin, cout, k, s, 0,
+                  ws.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, rm1.data_ptr(), rv1.data_ptr(), 0,
+                  sc1.data_ptr(), sh1.data_ptr(), S())
+    tiles = _lib.query("bpb_conv_num_mtiles", n, h, w)
+    stats = torch.empty(tiles, 2, cout, device=DEV)
+    _lib.call("bpb_conv_bf16", x.data_ptr(), wp.data_ptr(), y2.data_ptr(), stats.data_ptr(), n, h, w, cin, cout, k, s, 0, S())
+    _lib.call("bpb_bn_finalize", stats.data_ptr(), tiles, cout, 0, n * h * w, gamma.data_ptr(), beta.data_ptr(), 1e-5,
+              0.1, rm2.data_ptr(), rv2.data_ptr(), sc2.data_ptr(), sh2.data_ptr(), S())
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    assert rel_err(sc1, sc2) < 1e-5 and rel_err(sh1, sh2) < 1e-5 and rel_err(rm1, rm2) < 1e-5 and rel_err(rv1, rv2) < 1e-5
+    assert int(ws.count_nonzero()) == 0
+
+
 def test_conv_bn_hint_variants():
     n, h, w, cin, cout, k, s = 4, 32, 16, 64, 128, 3, 1
     g = torch.Generator().manual_seed(3)
