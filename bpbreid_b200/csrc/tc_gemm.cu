@@ -427,7 +427,13 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     BPB_CHECK(ho % bh == 0, "conv_bf16_tc: output height %d not a multiple of tile rows %d", ho, bh);
     const int bnimg = 128 / (wo * bh);
     BPB_CHECK(bnimg * wo * bh == 128, "conv_bf16_tc: tile does not cover 128 pixels (ho=%d wo=%d)", ho, wo);
-    const int kc = cin >= 64 ? 64 : 32;
+    // row-shift mode: 3x3 stride-1, tile inside one image, vertical tap offset = whole swizzle atoms (Wo % 8 == 0)
+    const bool rowshift = ksize == 3 && stride == 1 && bnimg == 1 && (wo % 8) == 0 && (bn_hint & 0x100) == 0;
+    bn_hint &= 0xFF;
+    // One thread can issue a tcgen05.mma only every ~98 cycles (tools/micro/umma_rate.cu), far slower than the
+    // 16/32-cycle math of the N=32/64 MMAs these narrow convolutions need, so MMA *issue* is the bound and the lever is
+    // the number of issuing CTAs per SM: 64-byte operand rows keep the ring stages small enough for 2-3 CTAs per SM.
+    const int kc = (rowshift || cin < 64) ? 32 : 64;
     BPB_CHECK(cin % kc == 0, "conv_bf16_tc: cin %d not a multiple of %d", cin, kc);
 
     GemmParams p{};
@@ -443,9 +449,6 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     p.out = y;
     p.stats = stats;
     p.bias = nullptr;
-    // row-shift mode: 3x3 stride-1, tile inside one image, vertical tap offset = whole swizzle atoms (Wo % 8 == 0)
-    const bool rowshift = ksize == 3 && stride == 1 && bnimg == 1 && (wo % 8) == 0 && (bn_hint & 0x100) == 0;
-    bn_hint &= 0xFF;
     p.mode = rowshift ? 3 : 0;
     p.a_rows = rowshift ? kTileM + 2 * wo : kTileM;
     p.rshift_bytes = rowshift ? wo * p.row_bytes : 0;
@@ -464,11 +467,12 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     }
     const int m_tiles = (p.M + kTileM - 1) / kTileM;
     int bn_tile = pick_bn(m_tiles, cout, bn_hint);
-    if (rowshift && bn_tile > 64 && p.row_bytes == 128) bn_tile = 64;      // keep >= 3 ring stages in shared memory
+    if (bn_hint == 0 && ksize == 3 && bn_tile > 64) bn_tile = 64;       // two issuing CTAs per SM beat one N=128 issuer
     {
+        const int target_ctas = bn_tile <= 32 ? 3 : 2;
         const int stage_bytes = (p.a_rows + (rowshift ? 3 : 1) * bn_tile) * p.row_bytes;
         const int epi_bytes = kTileM * (bn_tile * 2 + 16) + (bn ? 8 * cout : 0);
-        const int budget = !rowshift ? 72 * 1024 : (p.row_bytes == 64 ? 92 * 1024 : 150 * 1024 - epi_bytes);
+        const int budget = (227 * 1024) / target_ctas - 5 * 1024 - epi_bytes;
         p.stages = pick_stages(stage_bytes, budget);
     }
 
