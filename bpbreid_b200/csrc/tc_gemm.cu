@@ -18,7 +18,8 @@
 namespace bpb {
 
 constexpr int kTileM = 128;
-constexpr int kNumThreads = 192;
+constexpr int kMaxMmaWarps = 3;
+constexpr int kMaxThreads = 32 * (1 + kMaxMmaWarps + 4);
 
 struct GemmParams {
     int M;          // valid output rows (pixels)
@@ -32,6 +33,8 @@ struct GemmParams {
     int mode;       // 0: conv, one tap per stage   1: matrix (2-D A map)   2: part-concat matrix (3-D A map)
                     // 3: 3x3 stride-1 conv, three vertical taps per stage (row shift)
     int dchunks;    // mode 2: K chunks per part
+    int mma_warps;  // W: MMA-issuing warps per CTA; warp w owns ring stages g = w (mod W) and its own accumulator
+    int tmem_cols;  // power of two >= 2 * W * BN
     int a_rows;     // rows of the A stage: 128, or 128 + 2*Wo in mode 3
     int rshift_bytes;   // mode 3: bytes between vertically adjacent taps inside the A stage (Wo * row_bytes)
     int kwrap;      // elements after which the A channel coordinate wraps (cin for conv, K for matrix, D for parts)
@@ -66,7 +69,7 @@ enum Epi { EPI_RAW_STATS = 0, EPI_F32_BIAS = 1 };
 // address).  A-operand traffic from L2 drops from 9 to 3*(rows+2)/rows tiles per output tile and every ring stage
 // carries three taps' worth of MMAs, which amortises the single-thread issue loop.
 template <int BN, bool kTf32, int kEpi>
-__global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kMaxThreads) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     float* cta_stats = reinterpret_cast<float*>(epi_tile + kTileM * kPitch);   // [2][N] CTA-level column sums
     const bool fused_bn = kEpi == EPI_RAW_STATS && p.bn_acc != nullptr;
     if (fused_bn)
-        for (int i = threadIdx.x; i < 2 * p.N; i += kNumThreads) cta_stats[i] = 0.f;
+        for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) cta_stats[i] = 0.f;
 
     __shared__ uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
             mbar_init(&empty_bar[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_full[b], p.mma_warps);               // one commit per MMA warp and tile
             mbar_init(&acc_empty[b], 128);
         }
         fence_barrier_init();
@@ -111,7 +114,8 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
     }
-    if (warp == 1) tmem_alloc<2 * BN>(&tmem_base_smem);
+    const int W = p.mma_warps;
+    if (warp == 1) tmem_alloc_n(&tmem_base_smem, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -167,23 +171,31 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------ MMA issuer ------------------------------
+    } else if (warp <= W) {
+        // ------------------------------ MMA issuers (W warps) ------------------------------
+        // A single thread can issue one tcgen05.mma per ~100 cycles (tools/micro/umma_rate.cu), 3-6x slower than the
+        // 16/32-cycle math of the narrow N=32/64 tiles these convolutions need.  So W warps issue concurrently: warp w
+        // consumes ring stages g = w, w+W, ... and accumulates into ITS OWN TMEM tile (no cross-thread ordering is
+        // needed); the epilogue adds the W partial accumulators.  W divides k_iters, so every warp owns k_iters/W
+        // stages of every tile.
         constexpr uint32_t idesc = make_idesc(kTf32, kTileM, BN);
+        const int w = warp - 1;
         const int instrs = p.row_bytes >> 5;                   // 32 bytes of K per instruction (16 bf16 / 8 tf32)
         const uint64_t desc_hi = make_kmajor_desc(0, p.row_bytes);          // everything but the start address
         const uint32_t rshift16 = static_cast<uint32_t>(p.rshift_bytes) >> 4;
         const uint32_t btap16 = static_cast<uint32_t>(b_tap_bytes) >> 4;
-        int s = 0;
+        const int per_tile = p.k_iters / W;                    // stages this warp consumes per tile
+        int s = w;                                             // ring slot of this warp's next stage
         uint32_t ph = 0, lt = 0;
-        uint32_t stage_a = smem_a, fb = full_a, eb = empty_a;
+        while (s >= p.stages) { s -= p.stages; ph ^= 1; }
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const uint32_t buf = lt & 1, use = lt >> 1;
             mbar_wait_a(acce_a + buf * 8, (use & 1) ^ 1);
             tc_fence_after();
-            const uint32_t tacc = tmem_base + buf * BN;
-            for (int it = 0; it < p.k_iters; ++it) {
-                mbar_wait_a(fb, ph);
+            const uint32_t tacc = tmem_base + (buf * W + w) * BN;
+            for (int j = 0; j < per_tile; ++j) {
+                const uint32_t stage_a = smem_a + s * stage_bytes;
+                mbar_wait_a(full_a + s * 8, ph);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint64_t da = desc_hi | static_cast<uint64_t>((stage_a & 0x3FFFFu) >> 4);
@@ -191,20 +203,20 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                     for (int r = 0; r < taps; ++r)
                         for (int k = 0; k < instrs; ++k)
                             umma<kTf32>(tacc, da + r * rshift16 + 2 * k, db + r * btap16 + 2 * k, idesc,
-                                        (it > 0 || r > 0 || k > 0) ? 1u : 0u);
-                    umma_commit_a(eb);                          // smem slot free once these MMAs retire
-                    if (it == p.k_iters - 1) umma_commit_a(accf_a + buf * 8);
+                                        (j > 0 || r > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_a(empty_a + s * 8);            // smem slot free once these MMAs retire
+                    if (j == per_tile - 1) umma_commit_a(accf_a + buf * 8);
                 }
                 __syncwarp();
-                stage_a += stage_bytes; fb += 8; eb += 8;
-                if (++s == p.stages) { s = 0; ph ^= 1; stage_a = smem_a; fb = full_a; eb = empty_a; }
+                s += W;
+                while (s >= p.stages) { s -= p.stages; ph ^= 1; }
             }
         }
     } else {
-        // ------------------------------ epilogue (warps 2..5) ------------------------------
+        // ------------------------------ epilogue (4 warps after the MMA warps) ------------------------------
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;          // row of the tile == output pixel
-        const int et = (warp - 2) * 32 + lane;  // 0..127 epilogue thread id
+        const int et = (warp - 1 - W) * 32 + lane;  // 0..127 epilogue thread id
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int m_tile = t / n_tiles, n_tile = t % n_tiles;
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
             const int valid_rows = min(kTileM, p.M - m0);
             mbar_wait_a(accf_a + buf * 8, use & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * W * BN;
 
             if constexpr (kEpi == EPI_F32_BIAS) {
                 float* out = reinterpret_cast<float*>(p.out);
@@ -222,7 +234,14 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
-                    if (c0 + 32 >= BN) {                        // accumulator fully read: hand it back to the MMA warp
+                    for (int ww = 1; ww < W; ++ww) {            // add the other MMA warps' partial accumulators
+                        uint32_t u[32];
+                        tmem_ld32(taddr + ww * BN + c0, u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                    }
+                    if (c0 + 32 >= BN) {                        // accumulator fully read: hand it back to the MMA warps
                         tc_fence_before();
                         mbar_arrive_a(acce_a + buf * 8);
                     }
@@ -254,6 +273,13 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
                     uint32_t v[32];
                     tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
+                    for (int ww = 1; ww < W; ++ww) {
+                        uint32_t u[32];
+                        tmem_ld32(taddr + ww * BN + c0, u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                    }
                     if (c0 + 32 >= BN) {
                         tc_fence_before();
                         mbar_arrive_a(acce_a + buf * 8);
@@ -356,7 +382,7 @@ __global__ void __launch_bounds__(kNumThreads) tc_gemm_kernel(const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<2 * BN>(tmem_base);
+        tmem_dealloc_n(tmem_base, p.tmem_cols);
     }
 }
 
@@ -383,7 +409,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     // (shared memory is the binding limit: 56 registers x 192 threads allow 6 CTAs; the occupancy API under-reports
     //  here, so the bound is computed directly: 227 KB usable per SM, ~4 KB static + reserved per CTA)
     int per_sm = static_cast<int>((227 * 1024) / (smem + 4 * 1024));
-    if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);
+    if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
+    const int threads = 32 * (1 + p.mma_warps + 4);
+    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     static int num_sms = 0;
@@ -394,7 +422,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     }
     int grid = num_sms * per_sm;
     if (grid > total) grid = total;
-    kern<<<grid, kNumThreads, smem, stream>>>(tmA, tmB, p);
+    kern<<<grid, threads, smem, stream>>>(tmA, tmB, p);
     BPB_LAUNCH_CHECK("tc_gemm_kernel");
     return 0;
 }
@@ -405,6 +433,38 @@ static int pick_stages(int stage_bytes, int budget_bytes) {
     if (s > 8) s = 8;
     if (s < 2) s = 2;
     return s;
+}
+
+static int pow2_cols(int c) {
+    int v = 32;
+    while (v < c) v <<= 1;
+    return v;
+}
+
+// Pick the number of MMA-issuing warps W (must divide k_iters), the TMEM allocation and the ring depth so that
+// (issuers per SM) = W x (CTAs per SM) is maximal: TMEM allows 512 / pow2(2*W*BN) CTAs, shared memory the rest.
+static void choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_bytes) {
+    const int stage_bytes = (p.a_rows + taps * bn_tile) * p.row_bytes;
+    int best_w = 1, best_issuers = 0, best_ctas = 1;
+    for (int w = kMaxMmaWarps; w >= 1; --w) {
+        if (p.k_iters % w) continue;
+        const int cols = pow2_cols(2 * w * bn_tile);
+        if (cols > 512) continue;
+        int ctas = 512 / cols;
+        if (ctas > 3) ctas = 3;
+        // shared memory: at least 2 ring stages per CTA
+        while (ctas > 1 && (227 * 1024) / ctas - 5 * 1024 - epi_bytes < 2 * stage_bytes) --ctas;
+        const int issuers = w * ctas;
+        if (issuers > best_issuers) { best_issuers = issuers; best_w = w; best_ctas = ctas; }
+    }
+    p.mma_warps = best_w;
+    p.tmem_cols = pow2_cols(2 * best_w * bn_tile);
+    const int budget = (227 * 1024) / best_ctas - 5 * 1024 - epi_bytes;
+    int st = budget / stage_bytes;
+    if (st > 8) st = 8;
+    if (st < 2) st = 2;
+    if (st < best_w) st = best_w;            // every MMA warp needs a slot of its own in flight
+    p.stages = st;
 }
 
 static int pick_bn(int m_tiles, int cout, int bn_hint) {
@@ -467,14 +527,8 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     }
     const int m_tiles = (p.M + kTileM - 1) / kTileM;
     int bn_tile = pick_bn(m_tiles, cout, bn_hint);
-    if (bn_hint == 0 && ksize == 3 && bn_tile > 64) bn_tile = 64;       // two issuing CTAs per SM beat one N=128 issuer
-    {
-        const int target_ctas = bn_tile <= 32 ? 3 : 2;
-        const int stage_bytes = (p.a_rows + (rowshift ? 3 : 1) * bn_tile) * p.row_bytes;
-        const int epi_bytes = kTileM * (bn_tile * 2 + 16) + (bn ? 8 * cout : 0);
-        const int budget = (227 * 1024) / target_ctas - 5 * 1024 - epi_bytes;
-        p.stages = pick_stages(stage_bytes, budget);
-    }
+    if (bn_hint == 0 && ksize == 3 && bn_tile > 64) bn_tile = 64;       // narrow tiles + several issuers beat one N=128 issuer
+    choose_issue_config(p, bn_tile, (rowshift ? 3 : 1), kTileM * (bn_tile * 2 + 16) + (bn ? 8 * cout : 0));
 
     const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tmA, tmB;
@@ -522,7 +576,7 @@ int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bia
     const int m_tiles = (m + kTileM - 1) / kTileM;
     int bn = n >= 128 ? 128 : (n >= 64 ? 64 : 32);
     while (bn > 32 && m_tiles * ((n + bn - 1) / bn) < 148) bn >>= 1;
-    p.stages = pick_stages((kTileM + bn) * 128, 72 * 1024);
+    choose_issue_config(p, bn, 1, 0);
     CUtensorMap tmA, tmB;
     if (a_mode == 0) {
         BPB_CHECK(lda % 4 == 0 && lda >= k, "linear_tf32_tc: lda=%lld invalid", (long long)lda);
