@@ -23,7 +23,8 @@ _SIGS = {
     "bpb_conv_bn_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I, _P, _P, _P],
     "bpb_conv_bn_workspace_bytes": [_I],
     "bpb_conv_ref_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "bpb_stem_conv": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "bpb_stem_conv": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "bpb_stem_conv_tiles": [_I, _I, _I],
     "bpb_colstats_bf16": [_P, _P, _I, _I, _P],
     "bpb_colstats_tiles": [_I],
     "bpb_bn_finalize": [_P, _I, _I, _I, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P],
@@ -53,7 +54,7 @@ _SIGS = {
     "bpb_rank_market1501": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "bpb_argsort_rows": [_P, _I, _I, _P, _P],
 }
-_PLAIN_INT = {"bpb_conv_num_mtiles", "bpb_colstats_tiles", "bpb_abi_version"}
+_PLAIN_INT = {"bpb_conv_num_mtiles", "bpb_colstats_tiles", "bpb_abi_version", "bpb_stem_conv_tiles"}
 
 
 def header_symbols():

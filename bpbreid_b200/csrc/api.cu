@@ -94,10 +94,11 @@ int bpb_conv_ref_bf16(const void* x, const void* w, void* y, int n, int h, int w
                       int stride, void* stream) {
     return conv_ref(x, w, y, n, h, wd, cin, cout, ksize, stride, S(stream));
 }
-int bpb_stem_conv(const float* img, const float* w, void* y, int n, int h, int wd, int cout, int ksize, int stride,
-                  void* stream) {
-    return stem_conv(img, w, y, n, h, wd, cout, ksize, stride, S(stream));
+int bpb_stem_conv(const float* img, const float* w, void* y, float* partials, int n, int h, int wd, int cout, int ksize,
+                  int stride, void* stream) {
+    return stem_conv(img, w, y, partials, n, h, wd, cout, ksize, stride, S(stream));
 }
+int bpb_stem_conv_tiles(int n, int ho, int wo) { return stem_conv_tiles(n, ho, wo); }
 int bpb_colstats_bf16(const void* x, float* partials, int m, int c, void* stream) {
     return colstats_bf16(x, partials, m, c, nullptr, S(stream));
 }

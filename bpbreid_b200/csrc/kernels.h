@@ -25,8 +25,9 @@ int conv_num_mtiles(int n, int ho, int wo);
 // ---- nn_kernels.cu ----------------------------------------------------------------------------
 int conv_ref(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize, int stride,
              cudaStream_t stream);
-int stem_conv(const float* img, const float* w, void* y, int n, int h, int wd, int cout, int ksize, int stride,
-              cudaStream_t stream);
+int stem_conv(const float* img, const float* w, void* y, float* partials, int n, int h, int wd, int cout, int ksize,
+              int stride, cudaStream_t stream);
+int stem_conv_tiles(int n, int ho, int wo);
 int colstats_bf16(const void* x, float* partials, int m, int c, int* tiles_out, cudaStream_t stream);
 int colstats_tiles(int m);
 int bn_finalize(const float* partials, int tiles, int c, int c_lo, int64_t count, const float* gamma,

@@ -51,67 +51,134 @@ int conv_ref(const void* x, const void* w, void* y, int n, int h, int wd, int ci
 }
 
 // ----------------------------------------------------------------------------------------------
-// Stem convolution: NCHW fp32 image (3 channels) -> NHWC bf16 raw output.  Weights [cout][3][ks][ks] fp32
-// (PyTorch layout) are staged in shared memory; one thread produces 8 output channels of one pixel.
+// Stem convolution: NCHW fp32 image (3 channels) -> NHWC bf16 raw output + per-CTA BN partial sums.
+// One thread = one output pixel x 64 output channels: every weight read is a warp-wide shared-memory broadcast
+// (64 FMAs per 16 LDS.128), the 128-pixel tile is staged in shared memory so the global stores are fully
+// coalesced and the column statistics come from the bf16-rounded values exactly like the tensor-core conv.
+// Persistent grid: each CTA loops over tiles and emits ONE row of partials [2][64] (-> bpb_bn_finalize).
+// Weights: PyTorch layout [64][3][k][k] fp32.
 // ----------------------------------------------------------------------------------------------
+constexpr int kStemCout = 64;
+
 template <int KS>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w,
-                                                        __nv_bfloat16* __restrict__ y, int n, int h, int wd, int cout,
-                                                        int stride, int ho, int wo) {
-    extern __shared__ float ws[];                    // [3*KS*KS][cout]  (tap-major so 8 consecutive couts vectorise)
-    const int taps = 3 * KS * KS;
-    for (int i = threadIdx.x; i < taps * cout; i += blockDim.x) {
-        const int co = i % cout, t = i / cout;      // t = ci*KS*KS + r*KS + s
-        ws[i] = w[co * taps + t];
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                        __nv_bfloat16* __restrict__ y, float* __restrict__ partials,
+                                                        int n, int h, int wd, int stride, int ho, int wo) {
+    constexpr int kTaps = 3 * KS * KS;
+    constexpr int kPitch = kStemCout * 2 + 16;              // bytes per staged pixel row
+    extern __shared__ __align__(16) uint8_t stem_smem[];
+    float* ws = reinterpret_cast<float*>(stem_smem);        // [kTaps][64]
+    uint8_t* tile = stem_smem + kTaps * kStemCout * sizeof(float);      // [128][kPitch]
+    __shared__ float red[2][4][kStemCout];
+    for (int i = threadIdx.x; i < kTaps * kStemCout; i += blockDim.x) {
+        const int co = i % kStemCout, t = i / kStemCout;    // t = ci*KS*KS + r*KS + s
+        ws[i] = w[co * kTaps + t];
     }
+    float s_acc = 0.f, q_acc = 0.f;                          // thread t < 64: channel sums over this CTA's tiles
+    float s_acc2 = 0.f, q_acc2 = 0.f;
     __syncthreads();
-    const int groups = cout / 8;
-    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t total = static_cast<int64_t>(n) * ho * wo * groups;
-    if (idx >= total) return;
-    const int g = idx % groups;
-    const int64_t pix = idx / groups;
-    const int ox = pix % wo, oy = (pix / wo) % ho, im = pix / (static_cast<int64_t>(wo) * ho);
+    const int64_t total = static_cast<int64_t>(n) * ho * wo;
+    const int64_t tiles = (total + 127) / 128;
     constexpr int pad = KS / 2;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int ci = 0; ci < 3; ++ci) {
-        const float* plane = img + (static_cast<int64_t>(im) * 3 + ci) * h * wd;
+    for (int64_t tile_i = blockIdx.x; tile_i < tiles; tile_i += gridDim.x) {
+        const int64_t pix = tile_i * 128 + threadIdx.x;
+        const bool valid = pix < total;
+        float acc[kStemCout];
 #pragma unroll
-        for (int r = 0; r < KS; ++r) {
-            const int iy = oy * stride + r - pad;
-            if (iy < 0 || iy >= h) continue;
+        for (int j = 0; j < kStemCout; ++j) acc[j] = 0.f;
+        if (valid) {
+            const int ox = pix % wo, oy = (pix / wo) % ho, im = pix / (static_cast<int64_t>(wo) * ho);
+            for (int ci = 0; ci < 3; ++ci) {
+                const float* plane = img + (static_cast<int64_t>(im) * 3 + ci) * h * wd;
 #pragma unroll
-            for (int s = 0; s < KS; ++s) {
-                const int ix = ox * stride + s - pad;
-                if (ix < 0 || ix >= wd) continue;
-                // the image is consumed at bf16 precision like every other activation
-                const float v = __bfloat162float(__float2bfloat16(plane[iy * wd + ix]));
-                const float* wp = ws + ((ci * KS + r) * KS + s) * cout + g * 8;
+                for (int r = 0; r < KS; ++r) {
+                    const int iy = oy * stride + r - pad;
+                    if (iy < 0 || iy >= h) continue;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += v * wp[j];
+                    for (int sx = 0; sx < KS; ++sx) {
+                        const int ix = ox * stride + sx - pad;
+                        if (ix < 0 || ix >= wd) continue;
+                        // the image is consumed at bf16 precision like every other activation
+                        const float v = __bfloat162float(__float2bfloat16(plane[iy * wd + ix]));
+                        const float4* wp = reinterpret_cast<const float4*>(ws + ((ci * KS + r) * KS + sx) * kStemCout);
+#pragma unroll
+                        for (int j = 0; j < kStemCout / 4; ++j) {
+                            const float4 wv = wp[j];
+                            acc[4 * j + 0] += v * wv.x; acc[4 * j + 1] += v * wv.y;
+                            acc[4 * j + 2] += v * wv.z; acc[4 * j + 3] += v * wv.w;
+                        }
+                    }
+                }
             }
         }
+        uint4* trow = reinterpret_cast<uint4*>(tile + threadIdx.x * kPitch);
+#pragma unroll
+        for (int j = 0; j < kStemCout / 8; ++j) {
+            uint4 o;
+            o.x = pack_bf16(acc[8 * j + 0], acc[8 * j + 1]); o.y = pack_bf16(acc[8 * j + 2], acc[8 * j + 3]);
+            o.z = pack_bf16(acc[8 * j + 4], acc[8 * j + 5]); o.w = pack_bf16(acc[8 * j + 6], acc[8 * j + 7]);
+            trow[j] = o;
+        }
+        __syncthreads();
+        const int64_t left = total - tile_i * 128;
+        const int valid_rows = left < 128 ? static_cast<int>(left) : 128;
+        {   // column statistics: 32 channel pairs x 4 row groups
+            const int pair = threadIdx.x & 31, grp = threadIdx.x >> 5;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            for (int r = grp; r < valid_rows; r += 4) {
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(tile + r * kPitch + pair * 4);
+                const float a = bf16_lo(u), b = bf16_hi(u);
+                s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+            }
+            red[0][grp][pair * 2] = s0; red[0][grp][pair * 2 + 1] = s1;
+            red[1][grp][pair * 2] = q0; red[1][grp][pair * 2 + 1] = q1;
+        }
+        // coalesced stores: 8 x 16-byte chunks per pixel row
+        for (int ch = threadIdx.x; ch < 128 * 8; ch += 128) {
+            const int r = ch >> 3, cc = ch & 7;
+            if (r < valid_rows)
+                *reinterpret_cast<uint4*>(y + (tile_i * 128 + r) * kStemCout + cc * 8) =
+                    *reinterpret_cast<const uint4*>(tile + r * kPitch + cc * 16);
+        }
+        __syncthreads();
+        if (threadIdx.x < kStemCout) {
+            const int c = threadIdx.x;
+            s_acc += red[0][0][c] + red[0][1][c] + red[0][2][c] + red[0][3][c];
+            q_acc += red[1][0][c] + red[1][1][c] + red[1][2][c] + red[1][3][c];
+        }
+        (void)s_acc2; (void)q_acc2;
     }
-    uint4 o;
-    o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-    o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(y + pix * cout + g * 8) = o;
+    if (partials != nullptr && threadIdx.x < kStemCout) {
+        partials[static_cast<int64_t>(blockIdx.x) * 2 * kStemCout + threadIdx.x] = s_acc;
+        partials[static_cast<int64_t>(blockIdx.x) * 2 * kStemCout + kStemCout + threadIdx.x] = q_acc;
+    }
 }
 
-int stem_conv(const float* img, const float* w, void* y, int n, int h, int wd, int cout, int ksize, int stride,
-              cudaStream_t stream) {
+int stem_conv_tiles(int n, int ho, int wo) {
+    const int64_t tiles = (static_cast<int64_t>(n) * ho * wo + 127) / 128;
+    const int64_t grid = 148 * 4;
+    return static_cast<int>(tiles < grid ? tiles : grid);
+}
+
+int stem_conv(const float* img, const float* w, void* y, float* partials, int n, int h, int wd, int cout, int ksize,
+              int stride, cudaStream_t stream) {
     BPB_CHECK(ksize == 3 || ksize == 7, "stem_conv: ksize %d unsupported", ksize);
-    BPB_CHECK(cout % 8 == 0, "stem_conv: cout %d must be a multiple of 8", cout);
+    BPB_CHECK(cout == kStemCout, "stem_conv: cout %d unsupported (the stems of HRNet / ResNet have 64 channels)", cout);
     const int pad = ksize / 2;
     const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (wd + 2 * pad - ksize) / stride + 1;
-    const int64_t total = static_cast<int64_t>(n) * ho * wo * (cout / 8);
-    const size_t smem = static_cast<size_t>(3) * ksize * ksize * cout * sizeof(float);
+    const int grid = stem_conv_tiles(n, ho, wo);
+    const size_t smem = static_cast<size_t>(3) * ksize * ksize * cout * sizeof(float) + 128 * (kStemCout * 2 + 16);
     if (ksize == 3) {
-        stem_conv_kernel<3><<<ceil_div(total, 256), 256, smem, stream>>>(img, w, reinterpret_cast<__nv_bfloat16*>(y), n,
-                                                                         h, wd, cout, stride, ho, wo);
+        stem_conv_kernel<3><<<grid, 128, smem, stream>>>(img, w, reinterpret_cast<__nv_bfloat16*>(y), partials, n, h, wd,
+                                                         stride, ho, wo);
     } else {
-        stem_conv_kernel<7><<<ceil_div(total, 256), 256, smem, stream>>>(img, w, reinterpret_cast<__nv_bfloat16*>(y), n,
-                                                                         h, wd, cout, stride, ho, wo);
+        static bool configured = false;
+        if (!configured) {
+            BPB_CUDA(cudaFuncSetAttribute(stem_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            configured = true;
+        }
+        stem_conv_kernel<7><<<grid, 128, smem, stream>>>(img, w, reinterpret_cast<__nv_bfloat16*>(y), partials, n, h, wd,
+                                                         stride, ho, wo);
     }
     BPB_LAUNCH_CHECK("stem_conv_kernel");
     return 0;

@@ -444,27 +444,34 @@ static int pow2_cols(int c) {
 // Pick the number of MMA-issuing warps W (must divide k_iters), the TMEM allocation and the ring depth so that
 // (issuers per SM) = W x (CTAs per SM) is maximal: TMEM allows 512 / pow2(2*W*BN) CTAs, shared memory the rest.
 static void choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_bytes) {
+    // The ring depth must be a multiple of W: then every ring slot is always consumed by the same MMA warp, which is
+    // what the mbarrier parity protocol needs (a warp that shares a slot with another warp could skip a phase and
+    // mistake an old completion for the one it is waiting for).
     const int stage_bytes = (p.a_rows + taps * bn_tile) * p.row_bytes;
-    int best_w = 1, best_issuers = 0, best_ctas = 1;
+    const int kMaxSmem = 190 * 1024;
+    int best_w = 1, best_issuers = 0, best_stages = 2;
     for (int w = kMaxMmaWarps; w >= 1; --w) {
         if (p.k_iters % w) continue;
         const int cols = pow2_cols(2 * w * bn_tile);
         if (cols > 512) continue;
         int ctas = 512 / cols;
         if (ctas > 3) ctas = 3;
-        // shared memory: at least 2 ring stages per CTA
-        while (ctas > 1 && (227 * 1024) / ctas - 5 * 1024 - epi_bytes < 2 * stage_bytes) --ctas;
-        const int issuers = w * ctas;
-        if (issuers > best_issuers) { best_issuers = issuers; best_w = w; best_ctas = ctas; }
+        for (; ctas >= 1; --ctas) {
+            int budget = (227 * 1024) / ctas - 5 * 1024 - epi_bytes;
+            if (budget > kMaxSmem - epi_bytes) budget = kMaxSmem - epi_bytes;
+            int st = budget / stage_bytes;
+            if (st > 8) st = 8;
+            st = (st / w) * w;
+            const int min_st = w >= 2 ? w : 2;
+            if (st < min_st) continue;
+            const int issuers = w * ctas;
+            if (issuers > best_issuers) { best_issuers = issuers; best_w = w; best_stages = st; }
+            break;
+        }
     }
     p.mma_warps = best_w;
     p.tmem_cols = pow2_cols(2 * best_w * bn_tile);
-    const int budget = (227 * 1024) / best_ctas - 5 * 1024 - epi_bytes;
-    int st = budget / stage_bytes;
-    if (st > 8) st = 8;
-    if (st < 2) st = 2;
-    if (st < best_w) st = best_w;            // every MMA warp needs a slot of its own in flight
-    p.stages = st;
+    p.stages = best_stages;
 }
 
 static int pick_bn(int m_tiles, int cout, int bn_hint) {

@@ -318,9 +318,12 @@ class ForwardPlan:
         ho, wo = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
         raw = self._act(n, ho, wo, conv.out_channels)
         wt = conv.weight.detach()
-        self._op("bpb_stem_conv", self.images.data_ptr(), wt.data_ptr(), raw.t.data_ptr(), n, h, w, conv.out_channels,
-                 ksize, stride)
-        stats, tiles = (self.colstats(raw) if self.training else (None, 0))
+        stats, tiles = None, 0
+        if self.training:
+            tiles = _lib.query("bpb_stem_conv_tiles", n, ho, wo)
+            stats = self._small((tiles, 2, conv.out_channels))
+        self._op("bpb_stem_conv", self.images.data_ptr(), wt.data_ptr(), raw.t.data_ptr(), _lib.ptr(stats), n, h, w,
+                 conv.out_channels, ksize, stride)
         scale, shift = self.bn_scale_shift(stats, tiles, raw.c, raw.m, bn)
         y = self.apply(Lazy(raw, scale, shift), True)
         self._trace("stem", [conv, bn], [], [y], ksize=ksize, stride=stride)

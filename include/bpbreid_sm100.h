@@ -47,8 +47,10 @@ int bpb_conv_ref_bf16(const void* x, const void* w, void* y, int n, int h, int w
                       int stride, void* stream);
 /* Stem: NCHW fp32 image (3 ch) -> NHWC bf16 raw output; w is the PyTorch [cout,3,k,k] fp32 weight.
  * Replaces hrnet.py:533 (3x3 s2) and resnet.py:199-201 / resnet_fastreid.py:246 (7x7 s2). */
-int bpb_stem_conv(const float* img, const float* w, void* y, int n, int h, int wd, int cout, int ksize, int stride,
-                  void* stream);
+int bpb_stem_conv(const float* img, const float* w, void* y, float* partials, int n, int h, int wd, int cout, int ksize,
+                  int stride, void* stream);
+/* rows of `partials` ([rows, 2, 64] per-CTA column sums / sums of squares, may be NULL) written by bpb_stem_conv */
+int bpb_stem_conv_tiles(int n, int ho, int wo);
 /* Column statistics of a bf16 matrix [m, c] -> partials [bpb_colstats_tiles(m), 2, c]. */
 int bpb_colstats_bf16(const void* x, float* partials, int m, int c, void* stream);
 int bpb_colstats_tiles(int m);

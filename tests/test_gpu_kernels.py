@@ -231,10 +231,15 @@ def test_stem_and_maxpool():
         wt = (torch.randn(64, 3, k, k, generator=g) * 0.1).to(DEV)
         ho, wo = (h + 2 * (k // 2) - k) // 2 + 1, (w + 2 * (k // 2) - k) // 2 + 1
         y = torch.empty(n, ho, wo, 64, device=DEV, dtype=torch.bfloat16)
-        _lib.call("bpb_stem_conv", img.data_ptr(), wt.data_ptr(), y.data_ptr(), n, h, w, 64, k, 2, S())
+        rows = _lib.query("bpb_stem_conv_tiles", n, ho, wo)
+        part = torch.full((rows, 2, 64), float("nan"), device=DEV)
+        _lib.call("bpb_stem_conv", img.data_ptr(), wt.data_ptr(), y.data_ptr(), part.data_ptr(), n, h, w, 64, k, 2, S())
         torch.cuda.synchronize()
         ref = F.conv2d(img.to(torch.bfloat16).float(), wt, None, 2, k // 2)
         assert rel_err(y.float().permute(0, 3, 1, 2), ref) < 1e-2
+        yb = y.float().reshape(-1, 64)
+        st = part.sum(0)
+        assert rel_err(st[0], yb.sum(0)) < 1e-3 and rel_err(st[1], (yb * yb).sum(0)) < 1e-3
     x = torch.randn(n, 33, 17, 64, generator=g).to(torch.bfloat16).to(DEV)
     for pad, ceil in ((1, 0), (0, 1)):
         ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, pad, ceil_mode=bool(ceil))
