@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kMaxThreads) tc_gemm_kernel(const __grid_const
     if (fused_bn)
         for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) cta_stats[i] = 0.f;
 
-    __shared__ uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
+    __shared__ uint64_t full_bar[9], empty_bar[9], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float red_smem[2][8][BN < 32 ? 32 : BN];        // [sum|sq][row group][col]
 
@@ -450,23 +450,27 @@ static void choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_by
     const int stage_bytes = (p.a_rows + taps * bn_tile) * p.row_bytes;
     const int kMaxSmem = 190 * 1024;
     int best_w = 1, best_issuers = 0, best_stages = 2;
-    for (int w = kMaxMmaWarps; w >= 1; --w) {
-        if (p.k_iters % w) continue;
-        const int cols = pow2_cols(2 * w * bn_tile);
-        if (cols > 512) continue;
-        int ctas = 512 / cols;
-        if (ctas > 3) ctas = 3;
-        for (; ctas >= 1; --ctas) {
-            int budget = (227 * 1024) / ctas - 5 * 1024 - epi_bytes;
-            if (budget > kMaxSmem - epi_bytes) budget = kMaxSmem - epi_bytes;
-            int st = budget / stage_bytes;
-            if (st > 8) st = 8;
-            st = (st / w) * w;
-            const int min_st = w >= 2 ? w : 2;
-            if (st < min_st) continue;
-            const int issuers = w * ctas;
-            if (issuers > best_issuers) { best_issuers = issuers; best_w = w; best_stages = st; }
-            break;
+    // first pass: every MMA warp gets two ring slots (prefetch distance); second pass: one slot each
+    for (int slots_per_warp = 2; slots_per_warp >= 1 && best_issuers == 0; --slots_per_warp) {
+        for (int w = kMaxMmaWarps; w >= 1; --w) {
+            if (p.k_iters % w) continue;
+            const int cols = pow2_cols(2 * w * bn_tile);
+            if (cols > 512) continue;
+            int ctas = 512 / cols;
+            if (ctas > 3) ctas = 3;
+            for (; ctas >= 1; --ctas) {
+                int budget = (227 * 1024) / ctas - 5 * 1024 - epi_bytes;
+                if (budget > kMaxSmem - epi_bytes) budget = kMaxSmem - epi_bytes;
+                int st = budget / stage_bytes;
+                if (st > 9) st = 9;
+                st = (st / w) * w;
+                int min_st = slots_per_warp * w;
+                if (min_st < 2) min_st = 2;
+                if (st < min_st) continue;
+                const int issuers = w * ctas;
+                if (issuers > best_issuers) { best_issuers = issuers; best_w = w; best_stages = st; }
+                break;
+            }
         }
     }
     p.mma_warps = best_w;
@@ -500,7 +504,8 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     // One thread can issue a tcgen05.mma only every ~98 cycles (tools/micro/umma_rate.cu), far slower than the
     // 16/32-cycle math of the N=32/64 MMAs these narrow convolutions need, so MMA *issue* is the bound and the lever is
     // the number of issuing CTAs per SM: 64-byte operand rows keep the ring stages small enough for 2-3 CTAs per SM.
-    const int kc = (rowshift || cin < 64) ? 32 : 64;
+    // (128-byte rows move twice the bytes per TMA row request; measured: the C>=64 layers are faster with them)
+    const int kc = cin < 64 ? 32 : 64;
     BPB_CHECK(cin % kc == 0, "conv_bf16_tc: cin %d not a multiple of %d", cin, kc);
 
     GemmParams p{};
