@@ -208,7 +208,7 @@ int bpb_part_distance(const float* qf, const float* gf, const void* qv, const vo
                          S(stream));
 }
 int64_t bpb_part_distance_scratch_floats(int nq, int ng, int p) {
-    return 4 + static_cast<int64_t>(p) * (static_cast<int64_t>(nq) + ng);
+    return 4 + static_cast<int64_t>(p + 1) * (static_cast<int64_t>(nq) + ng);
 }
 int bpb_rank_market1501(const float* dist, const int64_t* q_pids, const int64_t* g_pids, const int64_t* q_camids,
                         const int64_t* g_camids, int nq, int ng, int max_rank, double* ap64, float* ap32,

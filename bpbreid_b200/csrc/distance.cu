@@ -18,8 +18,8 @@ enum { VIS_NONE = 0, VIS_BOOL = 1, VIS_FLOAT = 2 };
 enum { METRIC_EUCLIDEAN = 0, METRIC_COSINE = 1 };
 enum { STRAT_MEAN = 0, STRAT_MAX = 1 };
 
-// scratch layout (floats): [0] running max (float bits)  [1..] unused
-//                          then row norms: qs[P][Nq], gs[P][Ng]
+// scratch layout (floats): [0] running max (float bits)  [1..3] unused
+//                          then row norms qs[P][Nq], gs[P][Ng], then visibility bitmasks qmask[Nq], gmask[Ng] (u32)
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
     int* a = reinterpret_cast<int*>(addr);
@@ -163,214 +163,268 @@ __global__ void __launch_bounds__(256) part_distance_simt_kernel(
 }
 
 // ----------------------------------------------------------------------------------------------
-// tcgen05 path: CTA = 128 queries x 128 gallery rows, loop over parts; per part a tf32 K-loop (D/32 TMA stages)
-// accumulates q.g^T into one of two TMEM buffers while 8 epilogue warps drain the other one.
-// warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue (two warps per TMEM lane quarter, 64 columns each)
+// tcgen05 path.  Persistent CTAs (one per SM); a tile = 128 queries x 256 gallery rows, all P parts.
+//   warp 0      TMA producer: per K-chunk of 32 floats one 128x128B query box + one 256x128B gallery box (SW128)
+//   warp 1      MMA issuer: 4 x tcgen05.mma kind::tf32 M128 N256 K8 per chunk into one of two 256-column TMEM
+//               accumulators (part p+1 accumulates while part p drains)
+//   warps 2..17 epilogue: 4 warps per TMEM lane quarter, 64 columns each: sqrt / mask / running numerator in
+//               registers, part_dist row segments written straight from registers, combined distance at tile end
+// The kernel is bound by the L2 -> SM operand stream ((128+256) rows x D x 4 B per part per tile, ~9.7 GB at
+// 4096 x 16384 x 6 x 512 against a ~12 TB/s L2 fabric), not by HBM (2.1 GB) or the tensor pipe; the tile raster keeps
+// a group of 8 gallery tiles L2-resident while the query tiles stream past, so HBM sees every operand about once.
 // ----------------------------------------------------------------------------------------------
-constexpr int kDT = 128;           // tile edge (queries and gallery)
-constexpr int kDThreads = 320;
+constexpr int kDM = 128;           // queries per tile
+constexpr int kDN = 256;           // gallery rows per tile
 constexpr int kDStages = 4;
-constexpr int kDStageBytes = 2 * kDT * 128;
+constexpr int kDStageBytes = (kDM + kDN) * 128;
+constexpr int kDEpiWarps = 16;
+constexpr int kDEpiThreads = kDEpiWarps * 32;
+constexpr int kDThreads = 64 + kDEpiThreads;
+constexpr int kDMaxParts = 16;     // per-tile gallery vectors of all parts live in shared memory
+constexpr int kDGroup = 8;         // gallery tiles per raster group
+constexpr size_t kDSmemMax = kDStages * kDStageBytes + 1024 + (2 * kDMaxParts + 1) * kDN * 4;
 
 struct DistParams {
     int nq, ng, p, d, vis_mode, metric, strat;
     const void* qv; const void* gv;
     const float* qs; const float* gs;
+    const uint32_t* qmask; const uint32_t* gmask;
     float* dist; float* part_dist; float* scratch;
+    int tiles_q, tiles_g, num_tiles;
 };
 
-__global__ void __launch_bounds__(kDThreads) part_distance_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                     const __grid_constant__ CUtensorMap tmG,
-                                                                     const DistParams a) {
+__device__ __forceinline__ void dist_tile_coords(int t, int tiles_q, int tiles_g, int& tq, int& tg) {
+    const int group_sz = kDGroup * tiles_q;
+    const int grp = t / group_sz;
+    const int within = t - grp * group_sz;
+    const int g_in_grp = min(kDGroup, tiles_g - grp * kDGroup);
+    tq = within / g_in_grp;
+    tg = grp * kDGroup + (within - tq * g_in_grp);
+}
+
+// visibility bitmask per row (bit p = part p visible); boolean visibility only
+__global__ void __launch_bounds__(256) vis_mask_kernel(const uint8_t* __restrict__ v, int rows, int p,
+                                                       uint32_t* __restrict__ mask) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    uint32_t m = 0;
+    for (int pp = 0; pp < p; ++pp) m |= (v[static_cast<int64_t>(r) * p + pp] ? 1u : 0u) << pp;
+    mask[r] = m;
+}
+
+template <int kVis, bool kEuclid, bool kMax>
+__global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                        const __grid_constant__ CUtensorMap tmG,
+                                                                        const DistParams a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_gs = reinterpret_cast<float*>(smem + kDStages * kDStageBytes);      // [P][256] gallery |g|^2
+    float* s_gw = s_gs + a.p * kDN;                                               // [P][256] gallery visibility
+    uint32_t* s_gm = reinterpret_cast<uint32_t*>(s_gw + a.p * kDN);               // [256] gallery part bitmask
     __shared__ uint64_t full_bar[kDStages], empty_bar[kDStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float s_gs[2][kDT];          // |g|^2 of the current part (double buffered by part parity)
-    __shared__ float s_gvf[2][kDT];         // gallery visibility (as float) of the current part
-    __shared__ float s_max[8];
+    __shared__ float s_max[kDEpiWarps];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i0 = blockIdx.y * kDT, j0 = blockIdx.x * kDT;
-    const int kchunks = a.d / 32;
+    const int kchunks = a.d >> 5;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kDStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 256); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kDEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmG); }
-    if (warp == 1) tmem_alloc<256>(&tmem_base_smem);
+    if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t smem_a = smem_u32(smem);
+    const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
+    const uint32_t accf_a = smem_u32(&acc_full[0]), acce_a = smem_u32(&acc_empty[0]);
 
     if (warp == 0) {
         if (lane == 0) {
-            int it = 0;
-            for (int pp = 0; pp < a.p; ++pp) {
-                for (int kc = 0; kc < kchunks; ++kc, ++it) {
-                    const int s = it % kDStages;
-                    const uint32_t round = it / kDStages;
-                    mbar_wait(&empty_bar[s], (round & 1) ^ 1);
-                    uint8_t* dst = smem + s * kDStageBytes;
-                    mbar_expect_tx(&full_bar[s], kDStageBytes);
-                    tma_load_3d(dst, &tmQ, &full_bar[s], kc * 32, pp, i0);
-                    tma_load_3d(dst + kDT * 128, &tmG, &full_bar[s], kc * 32, pp, j0);
+            uint32_t s = 0, ph = 0;
+            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                int tq, tg;
+                dist_tile_coords(t, a.tiles_q, a.tiles_g, tq, tg);
+                const int i0 = tq * kDM, j0 = tg * kDN;
+                for (int pp = 0; pp < a.p; ++pp) {
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait_a(empty_a + s * 8, ph ^ 1);
+                        const uint32_t dst = smem_a + s * kDStageBytes;
+                        mbar_expect_tx_a(full_a + s * 8, kDStageBytes);
+                        tma_load_3d_a(dst, &tmQ, full_a + s * 8, kc * 32, pp, i0);
+                        tma_load_3d_a(dst + kDM * 128, &tmG, full_a + s * 8, kc * 32, pp, j0);
+                        if (++s == kDStages) { s = 0; ph ^= 1; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc(true, kDT, kDT);
-        int it = 0;
-        for (int pp = 0; pp < a.p; ++pp) {
-            const int buf = pp & 1;
-            const uint32_t use = pp >> 1;              // how many times this buffer has been used before
-            mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
-            tc_fence_after();
-            for (int kc = 0; kc < kchunks; ++kc, ++it) {
-                const int s = it % kDStages;
-                const uint32_t round = it / kDStages;
-                mbar_wait(&full_bar[s], round & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t q_addr = smem_u32(smem + s * kDStageBytes);
-                    const uint64_t dq = make_kmajor_desc(q_addr, 128);
-                    const uint64_t dg = make_kmajor_desc(q_addr + kDT * 128, 128);
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(true, kDM, kDN);
+            const uint64_t desc_hi = make_kmajor_desc(0, 128);
+            uint32_t s = 0, ph = 0, acc_it = 0;
+            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                for (int pp = 0; pp < a.p; ++pp, ++acc_it) {
+                    const uint32_t buf = acc_it & 1, use = acc_it >> 1;
+                    mbar_wait_a(acce_a + buf * 8, (use & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t tacc = tmem_base + buf * kDN;
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait_a(full_a + s * 8, ph);
+                        tc_fence_after();
+                        const uint32_t q_addr = smem_a + s * kDStageBytes;
+                        const uint64_t dq = desc_hi | static_cast<uint64_t>((q_addr & 0x3FFFFu) >> 4);
+                        const uint64_t dg = desc_hi | static_cast<uint64_t>(((q_addr + kDM * 128) & 0x3FFFFu) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma<true>(tmem_base + buf * kDT, dq + 2 * k, dg + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&empty_bar[s]);
-                    if (kc == kchunks - 1) umma_commit(&acc_full[buf]);
+                        for (int k = 0; k < 4; ++k)
+                            umma<true>(tacc, dq + 2 * k, dg + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                        umma_commit_a(empty_a + s * 8);
+                        if (kc == kchunks - 1) umma_commit_a(accf_a + buf * 8);
+                        if (++s == kDStages) { s = 0; ph ^= 1; }
+                    }
                 }
-                __syncwarp();
             }
         }
     } else {
-        const int ew = warp - 2;                 // 0..7
-        const int q = warp & 3;                  // TMEM lane quarter
-        const int half = ew >> 2;                // which 64-column half of the tile this warp drains
+        const int ew = warp - 2;                 // 0..15
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        const int cg = ew >> 2;                  // which 64-column group of the tile this warp drains
         const int row = q * 32 + lane;
-        const int i = i0 + row;
-        const bool row_ok = i < a.nq;
-        const int et = ew * 32 + lane;           // 0..255
-        float num[64];
-#pragma unroll
-        for (int t = 0; t < 64; ++t) num[t] = a.strat == STRAT_MAX ? -1.f : 0.f;
+        const int et = ew * 32 + lane;           // 0..511
         float local_max = -1.f;
-        for (int pp = 0; pp < a.p; ++pp) {
-            const int buf = pp & 1;
-            const uint32_t use = pp >> 1;
-            // stage per-part gallery-side vectors (256 epilogue threads, 128 entries each)
-            if (et < kDT) {
-                const int j = j0 + et;
-                s_gs[buf][et] = (j < a.ng && a.metric == METRIC_EUCLIDEAN) ? a.gs[static_cast<int64_t>(pp) * a.ng + j] : 0.f;
-            } else {
-                const int jj = et - kDT, j = j0 + jj;
-                float w = 1.f;
+        uint32_t acc_it = 0;
+        const bool vec_ok = (a.ng & 3) == 0;
+        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            int tq, tg;
+            dist_tile_coords(t, a.tiles_q, a.tiles_g, tq, tg);
+            const int i0 = tq * kDM, j0 = tg * kDN;
+            const int i = i0 + row;
+            const bool row_ok = i < a.nq;
+            const int jc = j0 + cg * 64;           // first gallery column of this thread
+            // ---- per-tile gallery-side vectors of all parts ----
+            asm volatile("bar.sync 1, %0;" ::"n"(kDEpiThreads) : "memory");       // previous tile done with them
+            for (int idx = et; idx < a.p * kDN; idx += kDEpiThreads) {
+                const int pp = idx >> 8, jj = idx & (kDN - 1), j = j0 + jj;
+                float gsv = 0.f, w = 1.f;
                 if (j < a.ng) {
-                    if (a.vis_mode == VIS_BOOL) w = reinterpret_cast<const uint8_t*>(a.gv)[static_cast<int64_t>(j) * a.p + pp] ? 1.f : 0.f;
-                    else if (a.vis_mode == VIS_FLOAT) w = reinterpret_cast<const float*>(a.gv)[static_cast<int64_t>(j) * a.p + pp];
+                    if (kEuclid) gsv = a.gs[static_cast<int64_t>(pp) * a.ng + j];
+                    if (kVis == VIS_BOOL) w = (a.gmask[j] >> pp) & 1u ? 1.f : 0.f;
+                    else if (kVis == VIS_FLOAT) w = reinterpret_cast<const float*>(a.gv)[static_cast<int64_t>(j) * a.p + pp];
                 }
-                s_gvf[buf][jj] = w;
+                s_gs[idx] = gsv;
+                s_gw[idx] = w;
             }
-            float qsv = 0.f, qw = 1.f;
-            if (row_ok) {
-                if (a.metric == METRIC_EUCLIDEAN) qsv = a.qs[static_cast<int64_t>(pp) * a.nq + i];
-                if (a.vis_mode == VIS_BOOL) qw = reinterpret_cast<const uint8_t*>(a.qv)[static_cast<int64_t>(i) * a.p + pp] ? 1.f : 0.f;
-                else if (a.vis_mode == VIS_FLOAT) qw = reinterpret_cast<const float*>(a.qv)[static_cast<int64_t>(i) * a.p + pp];
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            mbar_wait(&acc_full[buf], use & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kDT + half * 64;
+            if (et < kDN) s_gm[et] = (kVis == VIS_BOOL && j0 + et < a.ng) ? a.gmask[j0 + et] : 0xFFFFFFFFu;
+            asm volatile("bar.sync 1, %0;" ::"n"(kDEpiThreads) : "memory");
+            const uint32_t qm = (kVis == VIS_BOOL && row_ok) ? a.qmask[i] : 0xFFFFFFFFu;
+
+            float num[64];
 #pragma unroll
-            for (int cch = 0; cch < 2; ++cch) {
-                uint32_t v[32];
-                tmem_ld32(taddr + cch * 32, v);
-                tmem_ld_wait();
-                const int jb = half * 64 + cch * 32;
-                float o[32];
-#pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    const float dot = __uint_as_float(v[t]);
-                    float dv;
-                    if (a.metric == METRIC_EUCLIDEAN) dv = sqrtf(fmaxf(qsv - 2.f * dot + s_gs[buf][jb + t], 0.f));
-                    else dv = 1.f - dot;
-                    float w = 1.f;
-                    if (a.vis_mode == VIS_BOOL) w = qw * s_gvf[buf][jb + t];
-                    else if (a.vis_mode == VIS_FLOAT) w = sqrtf(qw * s_gvf[buf][jb + t]);
-                    const float pd_out = (a.vis_mode == VIS_BOOL && w == 0.f) ? -1.f : dv;
-                    o[t] = pd_out;
-                    if (j0 + jb + t < a.ng) local_max = fmaxf(local_max, pd_out);
-                    if (a.strat == STRAT_MAX) num[cch * 32 + t] = fmaxf(num[cch * 32 + t], a.vis_mode == VIS_NONE ? dv : pd_out);
-                    else num[cch * 32 + t] += dv * w;
+            for (int u = 0; u < 64; ++u) num[u] = kMax ? -1.f : 0.f;
+            for (int pp = 0; pp < a.p; ++pp, ++acc_it) {
+                const uint32_t buf = acc_it & 1, use = acc_it >> 1;
+                float qsv = 0.f, qw = 1.f;
+                if (row_ok) {
+                    if (kEuclid) qsv = a.qs[static_cast<int64_t>(pp) * a.nq + i];
+                    if (kVis == VIS_BOOL) qw = (qm >> pp) & 1u ? 1.f : 0.f;
+                    else if (kVis == VIS_FLOAT) qw = reinterpret_cast<const float*>(a.qv)[static_cast<int64_t>(i) * a.p + pp];
                 }
-                if (a.part_dist && row_ok) {
-                    float* dst = a.part_dist + (static_cast<int64_t>(pp) * a.nq + i) * a.ng + j0 + jb;
-                    if (j0 + jb + 32 <= a.ng && (a.ng & 3) == 0) {
+                const float* gs_p = s_gs + pp * kDN + cg * 64;
+                const float* gw_p = s_gw + pp * kDN + cg * 64;
+                float* prow = (a.part_dist && row_ok)
+                                  ? a.part_dist + (static_cast<int64_t>(pp) * a.nq + i) * a.ng + jc : nullptr;
+                mbar_wait_a(accf_a + buf * 8, use & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kDN + cg * 64;
 #pragma unroll
-                        for (int t = 0; t < 32; t += 4)
-                            *reinterpret_cast<float4*>(dst + t) = make_float4(o[t], o[t + 1], o[t + 2], o[t + 3]);
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < 32; ++t)
-                            if (j0 + jb + t < a.ng) dst[t] = o[t];
+                for (int cch = 0; cch < 4; ++cch) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + cch * 16, v);
+                    tmem_ld_wait();
+                    if (cch == 3) {                    // accumulator drained: hand the buffer back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_a(acce_a + buf * 8);
                     }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
-        }
-        if (!row_ok) local_max = -1.f;
-        // combined distance
-        if (row_ok) {
 #pragma unroll
-            for (int cch = 0; cch < 2; ++cch) {
-                const int jb = half * 64 + cch * 32;
-                float o[32];
+                    for (int u4 = 0; u4 < 16; u4 += 4) {
+                        float o[4];
 #pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    const int j = j0 + jb + t;
-                    float r = num[cch * 32 + t];
-                    if (a.strat != STRAT_MAX) {
-                        if (a.vis_mode == VIS_NONE) {
-                            r = r / static_cast<float>(a.p);
-                        } else if (j < a.ng) {
-                            float den = 0.f;
-                            for (int pp = 0; pp < a.p; ++pp) {
-                                if (a.vis_mode == VIS_BOOL) {
-                                    den += (reinterpret_cast<const uint8_t*>(a.qv)[static_cast<int64_t>(i) * a.p + pp] &&
-                                            reinterpret_cast<const uint8_t*>(a.gv)[static_cast<int64_t>(j) * a.p + pp]) ? 1.f : 0.f;
-                                } else {
-                                    den += sqrtf(reinterpret_cast<const float*>(a.qv)[static_cast<int64_t>(i) * a.p + pp] *
-                                                 reinterpret_cast<const float*>(a.gv)[static_cast<int64_t>(j) * a.p + pp]);
-                                }
+                        for (int e = 0; e < 4; ++e) {
+                            const int u = cch * 16 + u4 + e;
+                            const float dot = __uint_as_float(v[u4 + e]);
+                            float dv;
+                            if (kEuclid) dv = sqrtf(fmaxf(qsv - 2.f * dot + gs_p[u], 0.f));
+                            else dv = 1.f - dot;
+                            float w = 1.f;
+                            if (kVis == VIS_BOOL) w = qw * gw_p[u];
+                            else if (kVis == VIS_FLOAT) w = sqrtf(qw * gw_p[u]);
+                            const float pd_out = (kVis == VIS_BOOL && w == 0.f) ? -1.f : dv;
+                            o[e] = pd_out;
+                            if (jc + u < a.ng) local_max = fmaxf(local_max, pd_out);
+                            if (kMax) num[u] = fmaxf(num[u], kVis == VIS_NONE ? dv : pd_out);
+                            else num[u] += dv * w;
+                        }
+                        if (prow) {
+                            const int jb = jc + cch * 16 + u4;
+                            if (vec_ok && jb + 4 <= a.ng) {
+                                *reinterpret_cast<float4*>(prow + cch * 16 + u4) = make_float4(o[0], o[1], o[2], o[3]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (jb + e < a.ng) prow[cch * 16 + u4 + e] = o[e];
                             }
-                            r = den == 0.f ? -1.f : r / den;
                         }
                     }
-                    o[t] = r;
                 }
-                float* dst = a.dist + static_cast<int64_t>(i) * a.ng + j0 + jb;
-                if (j0 + jb + 32 <= a.ng && (a.ng & 3) == 0) {
+            }
+            // ---- combined distance ----
+            if (row_ok) {
+                float* drow = a.dist + static_cast<int64_t>(i) * a.ng + jc;
 #pragma unroll
-                    for (int t = 0; t < 32; t += 4)
-                        *reinterpret_cast<float4*>(dst + t) = make_float4(o[t], o[t + 1], o[t + 2], o[t + 3]);
-                } else {
+                for (int u4 = 0; u4 < 64; u4 += 4) {
+                    float o[4];
 #pragma unroll
-                    for (int t = 0; t < 32; ++t)
-                        if (j0 + jb + t < a.ng) dst[t] = o[t];
+                    for (int e = 0; e < 4; ++e) {
+                        const int u = u4 + e;
+                        float r = num[u];
+                        if (!kMax) {
+                            if (kVis == VIS_NONE) {
+                                r = r / static_cast<float>(a.p);
+                            } else if (kVis == VIS_BOOL) {
+                                const int den = __popc(qm & s_gm[cg * 64 + u]);
+                                r = den == 0 ? -1.f : r / static_cast<float>(den);
+                            } else {
+                                float den = 0.f;
+                                for (int pp = 0; pp < a.p; ++pp)
+                                    den += sqrtf(reinterpret_cast<const float*>(a.qv)[static_cast<int64_t>(i) * a.p + pp] *
+                                                 s_gw[pp * kDN + cg * 64 + u]);
+                                r = den == 0.f ? -1.f : r / den;
+                            }
+                        }
+                        o[e] = r;
+                    }
+                    const int jb = jc + u4;
+                    if (vec_ok && jb + 4 <= a.ng) {
+                        *reinterpret_cast<float4*>(drow + u4) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (jb + e < a.ng) drow[u4 + e] = o[e];
+                    }
                 }
             }
         }
         local_max = warp_max(local_max);
         if (lane == 0) s_max[ew] = local_max;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kDEpiThreads) : "memory");
         if (et == 0) {
             float m = s_max[0];
-            for (int t = 1; t < 8; ++t) m = fmaxf(m, s_max[t]);
+            for (int u = 1; u < kDEpiWarps; ++u) m = fmaxf(m, s_max[u]);
             atomic_max_float(a.scratch, m);
         }
         tc_fence_before();
@@ -378,49 +432,50 @@ __global__ void __launch_bounds__(kDThreads) part_distance_tc_kernel(const __gri
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<256>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
 }
 
 // ----------------------------------------------------------------------------------------------
 // Sparse fix-up: every -1 becomes max+1 (distance.py:173-176 / :214-217).  Positions are known from the
 // visibility vectors alone, so the big matrices are only written, never re-read.
+// Boolean visibility: one pass over (i, j) with the precomputed part bitmasks covers part_dist and dist.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fixup_part_kernel(float* __restrict__ part_dist, const uint8_t* __restrict__ qv,
-                                                         const uint8_t* __restrict__ gv, int nq, int ng, int p,
+__global__ void __launch_bounds__(256) fixup_bool_kernel(float* __restrict__ dist, float* __restrict__ part_dist,
+                                                         const uint32_t* __restrict__ qmask,
+                                                         const uint32_t* __restrict__ gmask, int nq, int ng, int p,
                                                          const float* __restrict__ scratch) {
-    const int pp = blockIdx.y, i = blockIdx.x;
+    const int i = blockIdx.x;
     const float mv = scratch[0] + 1.f;
-    float* row = part_dist + (static_cast<int64_t>(pp) * nq + i) * ng;
-    const bool qvis = qv[static_cast<int64_t>(i) * p + pp] != 0;
-    for (int j = threadIdx.x; j < ng; j += blockDim.x)
-        if (!qvis || gv[static_cast<int64_t>(j) * p + pp] == 0) row[j] = mv;
+    const uint32_t qm = qmask[i];
+    const uint32_t all = p >= 32 ? 0xFFFFFFFFu : ((1u << p) - 1u);
+    float* drow = dist + static_cast<int64_t>(i) * ng;
+    for (int j = threadIdx.x; j < ng; j += blockDim.x) {
+        const uint32_t vis = qm & gmask[j];
+        if (vis == 0) drow[j] = mv;
+        if (part_dist) {
+            uint32_t inv = ~vis & all;
+            while (inv) {
+                const int pp = __ffs(inv) - 1;
+                inv &= inv - 1;
+                part_dist[(static_cast<int64_t>(pp) * nq + i) * ng + j] = mv;
+            }
+        }
+    }
 }
 
-__global__ void __launch_bounds__(256) fixup_dist_kernel(float* __restrict__ dist, const void* __restrict__ qv,
-                                                         const void* __restrict__ gv, int vis_mode, int nq, int ng,
-                                                         int p, const float* __restrict__ scratch) {
+__global__ void __launch_bounds__(256) fixup_dist_float_kernel(float* __restrict__ dist, const float* __restrict__ qv,
+                                                               const float* __restrict__ gv, int nq, int ng, int p,
+                                                               const float* __restrict__ scratch) {
     const int i = blockIdx.x;
     const float mv = scratch[0] + 1.f;
     float* row = dist + static_cast<int64_t>(i) * ng;
-    if (vis_mode == VIS_BOOL) {
-        const uint8_t* q = reinterpret_cast<const uint8_t*>(qv) + static_cast<int64_t>(i) * p;
-        unsigned qm = 0;
-        for (int pp = 0; pp < p; ++pp) qm |= (q[pp] ? 1u : 0u) << pp;
-        for (int j = threadIdx.x; j < ng; j += blockDim.x) {
-            const uint8_t* g = reinterpret_cast<const uint8_t*>(gv) + static_cast<int64_t>(j) * p;
-            unsigned gm = 0;
-            for (int pp = 0; pp < p; ++pp) gm |= (g[pp] ? 1u : 0u) << pp;
-            if ((qm & gm) == 0) row[j] = mv;
-        }
-    } else {
-        const float* q = reinterpret_cast<const float*>(qv) + static_cast<int64_t>(i) * p;
-        for (int j = threadIdx.x; j < ng; j += blockDim.x) {
-            const float* g = reinterpret_cast<const float*>(gv) + static_cast<int64_t>(j) * p;
-            float den = 0.f;
-            for (int pp = 0; pp < p; ++pp) den += sqrtf(q[pp] * g[pp]);
-            if (den == 0.f) row[j] = mv;
-        }
+    const float* q = qv + static_cast<int64_t>(i) * p;
+    for (int j = threadIdx.x; j < ng; j += blockDim.x) {
+        const float* g = gv + static_cast<int64_t>(j) * p;
+        float den = 0.f;
+        for (int pp = 0; pp < p; ++pp) den += sqrtf(q[pp] * g[pp]);
+        if (den == 0.f) row[j] = mv;
     }
 }
 
@@ -435,39 +490,71 @@ int part_distance(const float* qf, const float* gf, const void* qv, const void* 
     BPB_CHECK(!(vis_mode == VIS_FLOAT && strat == STRAT_MAX), "part_distance: 'max' needs boolean visibility");
     float* qs = scratch + 4;
     float* gs = qs + static_cast<int64_t>(p) * nq;
+    uint32_t* qmask = reinterpret_cast<uint32_t*>(gs + static_cast<int64_t>(p) * ng);
+    uint32_t* gmask = qmask + nq;
     init_max_kernel<<<1, 1, 0, stream>>>(scratch);
-    const bool use_tc = impl != 1 && d % 32 == 0;
+    const bool use_tc = impl != 1 && d % 32 == 0 && p <= kDMaxParts;
     if (metric == METRIC_EUCLIDEAN) {
         sqnorm_kernel<<<ceil_div(static_cast<int64_t>(nq) * p, 8), 256, 0, stream>>>(qf, nq, p, d, use_tc ? 1 : 0, qs);
         sqnorm_kernel<<<ceil_div(static_cast<int64_t>(ng) * p, 8), 256, 0, stream>>>(gf, ng, p, d, use_tc ? 1 : 0, gs);
         BPB_LAUNCH_CHECK("sqnorm_kernel");
     }
+    if (vis_mode == VIS_BOOL) {
+        vis_mask_kernel<<<ceil_div(nq, 256), 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(qv), nq, p, qmask);
+        vis_mask_kernel<<<ceil_div(ng, 256), 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(gv), ng, p, gmask);
+        BPB_LAUNCH_CHECK("vis_mask_kernel");
+    }
     if (use_tc) {
         CUtensorMap tmQ, tmG;
-        uint32_t box[3] = {32, 1, (uint32_t)kDT};
         uint32_t es[3] = {1, 1, 1};
         {
+            uint32_t box[3] = {32, 1, (uint32_t)kDM};
             uint64_t dims[3] = {(uint64_t)d, (uint64_t)p, (uint64_t)nq};
             uint64_t strides[2] = {(uint64_t)d * 4, (uint64_t)p * d * 4};
             if (make_tensor_map(&tmQ, qf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dims, strides, box, es,
                                 CU_TENSOR_MAP_SWIZZLE_128B)) return 4;
         }
         {
+            uint32_t box[3] = {32, 1, (uint32_t)kDN};
             uint64_t dims[3] = {(uint64_t)d, (uint64_t)p, (uint64_t)ng};
             uint64_t strides[2] = {(uint64_t)d * 4, (uint64_t)p * d * 4};
             if (make_tensor_map(&tmG, gf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dims, strides, box, es,
                                 CU_TENSOR_MAP_SWIZZLE_128B)) return 4;
         }
-        DistParams a{nq, ng, p, d, vis_mode, metric, strat, qv, gv, qs, gs, dist, part_dist, scratch};
-        static bool configured = false;
-        const size_t smem = kDStages * kDStageBytes + 1024;
-        if (!configured) {
-            BPB_CUDA(cudaFuncSetAttribute(part_distance_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-            configured = true;
+        const int tiles_q = ceil_div(nq, kDM), tiles_g = ceil_div(ng, kDN);
+        DistParams a{nq, ng, p, d, vis_mode, metric, strat, qv, gv, qs, gs, qmask, gmask, dist, part_dist, scratch,
+                     tiles_q, tiles_g, tiles_q * tiles_g};
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            BPB_CUDA(cudaGetDevice(&dev));
+            BPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         }
-        dim3 grid(ceil_div(ng, kDT), ceil_div(nq, kDT));
-        part_distance_tc_kernel<<<grid, kDThreads, smem, stream>>>(tmQ, tmG, a);
+        const size_t smem = kDStages * kDStageBytes + 1024 + (2 * p + 1) * kDN * 4;
+        const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+        const bool eu = metric == METRIC_EUCLIDEAN, mx = strat == STRAT_MAX;
+#define BPB_DIST_LAUNCH(VIS, EU, MX)                                                                              \
+    do {                                                                                                          \
+        static bool configured = false;                                                                           \
+        if (!configured) {                                                                                        \
+            BPB_CUDA(cudaFuncSetAttribute(part_distance_tc_kernel<VIS, EU, MX>,                                   \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDSmemMax));          \
+            configured = true;                                                                                    \
+        }                                                                                                         \
+        part_distance_tc_kernel<VIS, EU, MX><<<grid, kDThreads, smem, stream>>>(tmQ, tmG, a);                     \
+    } while (0)
+#define BPB_DIST_VIS(VIS)                                                                                         \
+    do {                                                                                                          \
+        if (eu && !mx) BPB_DIST_LAUNCH(VIS, true, false);                                                         \
+        else if (eu && mx) BPB_DIST_LAUNCH(VIS, true, true);                                                      \
+        else if (!eu && !mx) BPB_DIST_LAUNCH(VIS, false, false);                                                  \
+        else BPB_DIST_LAUNCH(VIS, false, true);                                                                   \
+    } while (0)
+        if (vis_mode == VIS_NONE) BPB_DIST_VIS(VIS_NONE);
+        else if (vis_mode == VIS_BOOL) BPB_DIST_VIS(VIS_BOOL);
+        else BPB_DIST_VIS(VIS_FLOAT);
+#undef BPB_DIST_VIS
+#undef BPB_DIST_LAUNCH
         BPB_LAUNCH_CHECK("part_distance_tc_kernel");
     } else {
         dim3 grid(ceil_div(ng, kST), ceil_div(nq, kST));
@@ -475,15 +562,13 @@ int part_distance(const float* qf, const float* gf, const void* qv, const void* 
                                                             gs, dist, part_dist, scratch);
         BPB_LAUNCH_CHECK("part_distance_simt_kernel");
     }
-    if (vis_mode != VIS_NONE) {
-        if (vis_mode == VIS_BOOL && part_dist) {
-            dim3 g2(nq, p);
-            fixup_part_kernel<<<g2, 256, 0, stream>>>(part_dist, reinterpret_cast<const uint8_t*>(qv),
-                                                      reinterpret_cast<const uint8_t*>(gv), nq, ng, p, scratch);
-            BPB_LAUNCH_CHECK("fixup_part_kernel");
-        }
-        fixup_dist_kernel<<<nq, 256, 0, stream>>>(dist, qv, gv, vis_mode, nq, ng, p, scratch);
-        BPB_LAUNCH_CHECK("fixup_dist_kernel");
+    if (vis_mode == VIS_BOOL) {
+        fixup_bool_kernel<<<nq, 256, 0, stream>>>(dist, part_dist, qmask, gmask, nq, ng, p, scratch);
+        BPB_LAUNCH_CHECK("fixup_bool_kernel");
+    } else if (vis_mode == VIS_FLOAT) {
+        fixup_dist_float_kernel<<<nq, 256, 0, stream>>>(dist, reinterpret_cast<const float*>(qv),
+                                                        reinterpret_cast<const float*>(gv), nq, ng, p, scratch);
+        BPB_LAUNCH_CHECK("fixup_dist_float_kernel");
     }
     return 0;
 }

@@ -147,10 +147,29 @@ __global__ void __launch_bounds__(256) rank_finalize_kernel(const double* ap64, 
             run += hist[r];
             cmc[r] = nv > 0 ? static_cast<float>(run) / static_cast<float>(nv) : 0.f;
         }
-        double s = 0.0;
-        float s32 = 0.f;
-        for (int q = 0; q < nq; ++q)
-            if (first_rank[q] >= 0) { s += ap64[q]; s32 += ap32[q]; }
+    }
+    // mAP: the float32 sum must run in query order (rank_cy.pyx accumulates sequentially in float32), so one thread
+    // adds; the operands are staged through shared memory by the whole CTA so the serial chain never waits on DRAM.
+    __shared__ double s_ap64[1024];
+    __shared__ float s_ap32[1024];
+    double s = 0.0;
+    float s32 = 0.f;
+    for (int base = 0; base < nq; base += 1024) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < 1024 && base + k < nq; k += blockDim.x) {
+            const bool ok = first_rank[base + k] >= 0;
+            s_ap64[k] = ok ? ap64[base + k] : -1.0;
+            s_ap32[k] = ap32[base + k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int n = min(1024, nq - base);
+            for (int k = 0; k < n; ++k)
+                if (s_ap64[k] >= 0.0) { s += s_ap64[k]; s32 += s_ap32[k]; }
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int nv = nvalid_s;
         *map_out = nv > 0 ? s / nv : 0.0;
         *map32_out = nv > 0 ? s32 / static_cast<float>(nv) : 0.f;
     }

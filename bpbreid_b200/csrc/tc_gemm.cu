@@ -451,7 +451,8 @@ static void choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_by
     const int kMaxSmem = 190 * 1024;
     int best_w = 1, best_issuers = 0, best_stages = 2;
     // first pass: every MMA warp gets two ring slots (prefetch distance); second pass: one slot each
-    for (int slots_per_warp = 2; slots_per_warp >= 1 && best_issuers == 0; --slots_per_warp) {
+    // (a first pass that demanded two slots per warp was measured slower: it trades CTAs per SM for ring depth)
+    for (int slots_per_warp = 1; slots_per_warp >= 1 && best_issuers == 0; --slots_per_warp) {
         for (int w = kMaxMmaWarps; w >= 1; --w) {
             if (p.k_iters % w) continue;
             const int cols = pow2_cols(2 * w * bn_tile);
@@ -504,8 +505,9 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     // One thread can issue a tcgen05.mma only every ~98 cycles (tools/micro/umma_rate.cu), far slower than the
     // 16/32-cycle math of the N=32/64 MMAs these narrow convolutions need, so MMA *issue* is the bound and the lever is
     // the number of issuing CTAs per SM: 64-byte operand rows keep the ring stages small enough for 2-3 CTAs per SM.
-    // (128-byte rows move twice the bytes per TMA row request; measured: the C>=64 layers are faster with them)
-    const int kc = cin < 64 ? 32 : 64;
+    // 64-byte rows for the row-shift schedule: smaller ring stages -> two issuing CTAs per SM (measured faster
+    // than 128-byte rows with one CTA per SM: 15.3 vs 16.2 ms per step)
+    const int kc = (rowshift || cin < 64) ? 32 : 64;
     BPB_CHECK(cin % kc == 0, "conv_bf16_tc: cin %d not a multiple of %d", cin, kc);
 
     GemmParams p{};
