@@ -159,6 +159,12 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// whole-warp wait with a single polling lane: the other 31 lanes park at the warp barrier instead of hammering the
+// mbarrier (a dozen spinning warps per CTA otherwise compete with TMA / UMMA / epilogue shared-memory traffic)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, bool leader) {
+    if (leader) mbar_wait_a(bar, parity);
+    __syncwarp();
+}
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -187,6 +193,25 @@ __device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+
+// One elected lane of a fully converged warp (elect.sync).  Issue loops are written so that the WHOLE warp runs the
+// control flow with warp-uniform values and only the tcgen05 / TMA instruction itself is predicated on the elected
+// lane: then ptxas keeps descriptors and coordinates in uniform registers.  A loop nested under `if (lane == 0)`
+// instead makes every UTCHMMA / UTMALDG a vote + ELECT + 5x R2UR "waterfall" (~100 cycles per tcgen05.mma, ~300 per
+// TMA box: tools/micro/umma_rate.cu, tma_rate.cu).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index as a provably warp-uniform value (the shuffle is what tells the compiler)
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
 
 // ---- tcgen05 ----
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_max[kDEpiWarps];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int kchunks = a.d >> 5;
 
     if (threadIdx.x == 0) {
@@ -238,13 +238,16 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);     // warp-uniform
     const uint32_t smem_a = smem_u32(smem);
     const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
     const uint32_t accf_a = smem_u32(&acc_full[0]), acce_a = smem_u32(&acc_empty[0]);
 
     if (warp == 0) {
-        if (lane == 0) {
+        // all 32 lanes run the (warp-uniform) control flow, the elected lane issues: keeps TMA / MMA operands in
+        // uniform registers (see elect_one_sync in common.cuh)
+        const bool leader = elect_one_sync();
+        {
             uint32_t s = 0, ph = 0;
             for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
                 int tq, tg;
@@ -254,16 +257,19 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait_a(empty_a + s * 8, ph ^ 1);
                         const uint32_t dst = smem_a + s * kDStageBytes;
-                        mbar_expect_tx_a(full_a + s * 8, kDStageBytes);
-                        tma_load_3d_a(dst, &tmQ, full_a + s * 8, kc * 32, pp, i0);
-                        tma_load_3d_a(dst + kDM * 128, &tmG, full_a + s * 8, kc * 32, pp, j0);
+                        if (leader) {
+                            mbar_expect_tx_a(full_a + s * 8, kDStageBytes);
+                            tma_load_3d_a(dst, &tmQ, full_a + s * 8, kc * 32, pp, i0);
+                            tma_load_3d_a(dst + kDM * 128, &tmG, full_a + s * 8, kc * 32, pp, j0);
+                        }
                         if (++s == kDStages) { s = 0; ph ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        const bool leader = elect_one_sync();
+        {
             constexpr uint32_t idesc = make_idesc(true, kDM, kDN);
             const uint64_t desc_hi = make_kmajor_desc(0, 128);
             uint32_t s = 0, ph = 0, acc_it = 0;
@@ -279,11 +285,14 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
                         const uint32_t q_addr = smem_a + s * kDStageBytes;
                         const uint64_t dq = desc_hi | static_cast<uint64_t>((q_addr & 0x3FFFFu) >> 4);
                         const uint64_t dg = desc_hi | static_cast<uint64_t>(((q_addr + kDM * 128) & 0x3FFFFu) >> 4);
+                        if (leader) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma<true>(tacc, dq + 2 * k, dg + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                        umma_commit_a(empty_a + s * 8);
-                        if (kc == kchunks - 1) umma_commit_a(accf_a + buf * 8);
+                            for (int k = 0; k < 4; ++k)
+                                umma<true>(tacc, dq + 2 * k, dg + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            umma_commit_a(empty_a + s * 8);
+                            if (kc == kchunks - 1) umma_commit_a(accf_a + buf * 8);
+                        }
+                        __syncwarp();
                         if (++s == kDStages) { s = 0; ph ^= 1; }
                     }
                 }

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu > gpurun_out/pytest_kernels.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_kernels.log
+timeout 300 python tools/probe_conv.py all > gpurun_out/probe_conv.log 2>&1; tail -12 gpurun_out/probe_conv.log
+timeout 600 python bench.py --steps 10 --warmup 3 --skip-cpu > gpurun_out/bench10.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench10.log | cut -c1-200
