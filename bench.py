@@ -258,7 +258,7 @@ def run_gpu_arm(args, rank, world):
         step_device()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        print(json.dumps({"profile": "one step", "launches": sum(KERNELS_PER_CALL.get(n_, 1) for _, _, n_ in plan.ops)}))
+        print(json.dumps({"profile": "one step", "launches": sum(KERNELS_PER_CALL.get(op[2], 1) for op in plan.ops if op[0] is not None)}))
         return
     sampler = ClockSampler(local)
     if rank == 0:
@@ -294,7 +294,7 @@ def run_gpu_arm(args, rank, world):
         return
     ms_per_step = dev_ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
-    launches_per_step = sum(KERNELS_PER_CALL.get(name, 1) for _, _, name in plan.ops) + 3 * 2 + 3 + 1 + 2
+    launches_per_step = sum(KERNELS_PER_CALL.get(op[2], 1) for op in plan.ops if op[0] is not None) + 3 * 2 + 3 + 1 + 2
     roof = roofline_probe(dev, peaks)
     cpu_ips, cpu_dt = time_cpu_port(32, 2, 1) if not args.skip_cpu else (None, None)
     line = {

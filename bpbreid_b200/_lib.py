@@ -20,7 +20,6 @@ _F = ctypes.c_float
 _SIGS = {
     "bpb_conv_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpb_conv_num_mtiles": [_I, _I, _I],
-    "bpb_conv_set_profile_buffer": [_P],
     "bpb_conv_bn_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I, _P, _P, _P],
     "bpb_conv_bn_workspace_bytes": [_I],
     "bpb_conv_ref_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -81,10 +81,6 @@ int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, in
                   int ksize, int stride, int bn_hint, void* stream) {
     return conv_bf16_tc(x, w, y, stats, n, h, wd, cin, cout, ksize, stride, bn_hint, nullptr, S(stream));
 }
-int bpb_conv_set_profile_buffer(void* buf) {
-    conv_set_profile_buffer(reinterpret_cast<long long*>(buf));
-    return 0;
-}
 int bpb_conv_bn_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                      int ksize, int stride, int bn_hint, void* bn_workspace, const float* gamma, const float* beta,
                      float eps, float momentum, float* running_mean, float* running_var, int c_lo, float* scale,

@@ -8,11 +8,8 @@
 // out-of-bounds fill and stride-2 convolutions from the map's element strides -- or a plain row-major
 // matrix [M, K] (bf16, or fp32 consumed as tf32).  B is the weight matrix [Cout, taps*Cin], K-major.
 //
-// Roles: warp 0 = TMA producer (A operand), warps 1..W = MMA issuers (warp 1 also owns the TMEM allocation),
-// next 4 warps = epilogue (TMEM -> registers -> smem tile -> coalesced global stores + BN partial sums),
-// last 0..3 warps = B-operand TMA producers.  One thread can start a TMA box only every ~260-330 cycles
-// (tools/micro/tma_rate.cu, profiles/tma_rate_r1.txt), so the weight matrix is either loaded ONCE per CTA
-// ("B resident", whenever it fits beside the ring) or streamed by its own producer warps in parallel with A.
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> smem tile -> coalesced global stores + BN partial sums).
 // Reference semantics replaced: nn.Conv2d / nn.Linear call sites of torchreid/models/hrnet.py:67-137,
 // 211-257,449-483, torchreid/models/resnet.py:105-154, torchreid/models/bpbreid.py:324-350,398-415.
 #include "common.cuh"
@@ -22,9 +19,7 @@ namespace bpb {
 
 constexpr int kTileM = 128;
 constexpr int kMaxMmaWarps = 3;
-constexpr int kMaxBProducers = 3;
-constexpr int kMaxWarps = 13;                              // 2 CTAs x 13 warps x 78 registers fit the register file
-constexpr int kMaxThreads = 32 * kMaxWarps;
+constexpr int kMaxThreads = 32 * (1 + kMaxMmaWarps + 4);
 
 struct GemmParams {
     int M;          // valid output rows (pixels)
@@ -41,10 +36,6 @@ struct GemmParams {
     int mma_warps;  // W: MMA-issuing warps per CTA; warp w owns ring stages g = w (mod W) and its own accumulator
     int tmem_cols;  // power of two >= 2 * W * BN
     int a_rows;     // rows of the A stage: 128, or 128 + 2*Wo in mode 3
-    int b_resident; // 1: the whole weight matrix is loaded into shared memory once per CTA (ring stages carry A only)
-    int b_res_bytes;    // n_tiles * ksteps * BN * row_bytes
-    int ksteps;     // K steps (taps * channel chunks) of one output tile == B tiles per n-tile
-    int b_producers;    // streaming B: extra warps whose lane 0 issues the B boxes (0: the A producer issues them too)
     int rshift_bytes;   // mode 3: bytes between vertically adjacent taps inside the A stage (Wo * row_bytes)
     int kwrap;      // elements after which the A channel coordinate wraps (cin for conv, K for matrix, D for parts)
     int ksize, stride, pad, Ho, Wo;
@@ -63,49 +54,9 @@ struct GemmParams {
     float eps, momentum;
     double inv_count, unbias;
     int c_lo;
-    long long* prof;    // diagnostic: per-role cycle counters of CTA 0 ([16][8] int64), or null
 };
 
 enum Epi { EPI_RAW_STATS = 0, EPI_F32_BIAS = 1 };
-
-// named barrier of one 128-thread epilogue group (immediate ids keep the kernel's barrier count at 4)
-__device__ __forceinline__ void epi_group_barrier(int grp_id) {
-    if (grp_id == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-    else asm volatile("bar.sync 2, 128;" ::: "memory");
-}
-
-// Column sums of a 32-row x 16-column register tile held one row per lane: recursive halving (16 shuffles instead of
-// 16 x 5), after which every lane pair (l, l^1) holds the total of column ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 +
-// ((l>>1)&1).
-__device__ __forceinline__ float warp_colsum16(const float (&x)[16], int lane) {
-    constexpr unsigned kFull = 0xffffffffu;
-    float a[8], b[4], c[2];
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float mine = h16 ? x[8 + i] : x[i], other = h16 ? x[i] : x[8 + i];
-        a[i] = mine + __shfl_xor_sync(kFull, other, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float mine = h8 ? a[4 + i] : a[i], other = h8 ? a[i] : a[4 + i];
-        b[i] = mine + __shfl_xor_sync(kFull, other, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float mine = h4 ? b[2 + i] : b[i], other = h4 ? b[i] : b[2 + i];
-        c[i] = mine + __shfl_xor_sync(kFull, other, 4);
-    }
-    const float mine = h2 ? c[1] : c[0], other = h2 ? c[0] : c[1];
-    float d = mine + __shfl_xor_sync(kFull, other, 2);
-    d += __shfl_xor_sync(kFull, d, 1);
-    return d;
-}
-
-static long long* g_prof = nullptr;
-void conv_set_profile_buffer(long long* buf) { g_prof = buf; }
-
-#define PROF_T() (prof ? clock64() : 0ll)
 
 // Persistent, warp-specialised kernel: each CTA walks output tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest so
 // consecutive tiles share their A rows in L2).  The TMA producer runs ahead across tile boundaries through the smem
@@ -118,47 +69,35 @@ void conv_set_profile_buffer(long long* buf) { g_prof = buf; }
 // address).  A-operand traffic from L2 drops from 9 to 3*(rows+2)/rows tiles per output tile and every ring stage
 // carries three taps' worth of MMAs, which amortises the single-thread issue loop.
 template <int BN, bool kTf32, int kEpi>
-__global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kMaxThreads) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
-    const long long t_entry = p.prof ? clock64() : 0ll;
-    if (p.prof && threadIdx.x == 0 && blockIdx.x < 600) {      // diagnostic: CTA residency timeline
-        unsigned long long ns; unsigned smid;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        p.prof[128 + blockIdx.x * 4 + 0] = static_cast<long long>(ns);
-        p.prof[128 + blockIdx.x * 4 + 2] = smid;
-    }
     const int taps = p.mode == 3 ? 3 : 1;                      // taps (MMA groups) per ring stage
     const int a_bytes = p.a_rows * p.row_bytes;
     const int b_tap_bytes = BN * p.row_bytes;
-    const int stage_bytes = p.b_resident ? a_bytes : a_bytes + taps * b_tap_bytes;
+    const int stage_bytes = a_bytes + taps * b_tap_bytes;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int m_tiles = (p.M + kTileM - 1) / kTileM;
     const int total_tiles = m_tiles * n_tiles;
-    constexpr int kEG = BN <= 64 ? 2 : 1;                      // epilogue groups (4 warps each)
     constexpr int kPitch = BN * 2 + 16;                        // epilogue staging tile row pitch (bytes)
-    uint8_t* b_res = smem + p.stages * stage_bytes;            // resident weight tiles [n_tile][kstep][BN][row_bytes]
-    uint8_t* epi_tile = b_res + p.b_res_bytes;                 // [128][kPitch], RAW_STATS only
-    float* cta_stats = reinterpret_cast<float*>(epi_tile + kEG * kTileM * kPitch);   // [kEG][2][N] CTA-level column sums
+    uint8_t* epi_tile = smem + p.stages * stage_bytes;         // [128][kPitch], RAW_STATS only
+    float* cta_stats = reinterpret_cast<float*>(epi_tile + kTileM * kPitch);   // [2][N] CTA-level column sums
     const bool fused_bn = kEpi == EPI_RAW_STATS && p.bn_acc != nullptr;
-    const int cta_stats_floats = 2 * p.N > 8 * BN ? 2 * p.N : 8 * BN;     // per group: [2][N] or [4 warps][2][BN]
     if (fused_bn)
-        for (int i = threadIdx.x; i < kEG * cta_stats_floats; i += blockDim.x) cta_stats[i] = 0.f;
+        for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) cta_stats[i] = 0.f;
 
-    __shared__ uint64_t full_bar[9], empty_bar[9], acc_full[2], acc_empty[2], b_full;
+    __shared__ uint64_t full_bar[9], empty_bar[9], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float red_smem[kEG][2][8][BN < 32 ? 32 : BN];   // [epilogue group][sum|sq][row group][col]
+    __shared__ float red_smem[2][8][BN < 32 ? 32 : BN];        // [sum|sq][row group][col]
 
     // shared-window addresses, computed once
     const uint32_t smem_a = smem_u32(smem);
     const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
     const uint32_t accf_a = smem_u32(&acc_full[0]), acce_a = smem_u32(&acc_empty[0]);
-    const uint32_t bfull_a = smem_u32(&b_full), b_res_a = smem_u32(b_res);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -167,11 +106,9 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_co
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], p.mma_warps);               // one commit per MMA warp and tile
-            mbar_init(&acc_empty[b], 128);                      // the 128 threads of the epilogue group draining it
+            mbar_init(&acc_empty[b], 128);
         }
-        mbar_init(&b_full, 1);
         fence_barrier_init();
-        if (p.b_resident) mbar_expect_tx_a(bfull_a, p.b_res_bytes);
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -183,29 +120,14 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);     // warp-uniform
-    if (p.prof && threadIdx.x == 0 && blockIdx.x == 0) p.prof[15 * 8 + 0] = clock64() - t_entry;   // setup cycles
-
-    if (p.b_resident && warp >= 1 && elect_one_sync()) {
-        // one-time load of the whole weight matrix, the boxes spread over every warp but the A producer
-        const int nw = (blockDim.x >> 5) - 1;
-        const int total_b = n_tiles * p.ksteps;
-        for (int idx = warp - 1; idx < total_b; idx += nw) {
-            const int nt = idx / p.ksteps, j = idx - nt * p.ksteps;
-            tma_load_2d_a(b_res_a + idx * b_tap_bytes, &tmB, bfull_a, j * p.kc, nt * BN);
-        }
-    }
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         {
             // NOTE: this loop paces the whole CTA: no integer division / modulo and no address-of-shared inside
             // (measured: `g % stages`, `it / kchunks` made an iteration cost ~1450 cycles).  All 32 lanes run the
-            // (warp-uniform) control flow; only the elected lane issues.
+            // warp-uniform control flow, the elected lane issues (see elect_one_sync in common.cuh).
             const bool leader = elect_one_sync();
-            const bool own_b = !p.b_resident && p.b_producers == 0;
-            long long* prof = (p.prof && blockIdx.x == 0) ? p.prof : nullptr;
-            long long t_wait = 0, t_issue = 0;
-            const long long t_begin = PROF_T();
             int s = 0;
             uint32_t ph = 0;                                    // parity of the ring round
             uint32_t stage_a = smem_a, fb = full_a, eb = empty_a;
@@ -221,20 +143,15 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_co
                 const int m0 = m_tile * kTileM, nb0 = n_tile * BN;
                 int tap_r = 0, tap_s = 0, kc = 0, bk = 0, part = 0;
                 for (int it = 0; it < p.k_iters; ++it) {
-                    const long long t0 = PROF_T();
-                    mbar_wait_warp(eb, ph ^ 1, leader);
-                    const long long t1 = PROF_T();
-                    t_wait += t1 - t0;
+                    mbar_wait_a(eb, ph ^ 1);
                     if (leader) {
                     mbar_expect_tx_a(fb, stage_bytes);
                     if (p.mode == 3) {
                         tma_load_4d_a(stage_a, &tmA, fb, kc, tap_s - 1, hbase, n0);
-                        if (own_b) {
-                            const int col = tap_s * p.cin + kc;      // tap (r, s) lives at column (3 r + s) * cin + kc
-                            tma_load_2d_a(stage_a + a_bytes, &tmB, fb, col, nb0);
-                            tma_load_2d_a(stage_a + a_bytes + b_tap_bytes, &tmB, fb, col + 3 * p.cin, nb0);
-                            tma_load_2d_a(stage_a + a_bytes + 2 * b_tap_bytes, &tmB, fb, col + 6 * p.cin, nb0);
-                        }
+                        const int col = tap_s * p.cin + kc;          // tap (r, s) lives at column (3 r + s) * cin + kc
+                        tma_load_2d_a(stage_a + a_bytes, &tmB, fb, col, nb0);
+                        tma_load_2d_a(stage_a + a_bytes + b_tap_bytes, &tmB, fb, col + 3 * p.cin, nb0);
+                        tma_load_2d_a(stage_a + a_bytes + 2 * b_tap_bytes, &tmB, fb, col + 6 * p.cin, nb0);
                     } else {
                         if (p.mode == 0) {
                             tma_load_4d_a(stage_a, &tmA, fb, kc, tap_s - p.pad, hbase + tap_r, n0);
@@ -243,7 +160,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_co
                         } else {
                             tma_load_3d_a(stage_a, &tmA, fb, kc, m0, part);
                         }
-                        if (own_b) tma_load_2d_a(stage_a + a_bytes, &tmB, fb, bk, nb0);
+                        tma_load_2d_a(stage_a + a_bytes, &tmB, fb, bk, nb0);
                     }
                     }
                     bk += p.kc;                                 // B columns advance contiguously: tap*cin + kc
@@ -255,10 +172,8 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_co
                     }
                     stage_a += stage_bytes; fb += 8; eb += 8;
                     if (++s == p.stages) { s = 0; ph ^= 1; stage_a = smem_a; fb = full_a; eb = empty_a; }
-                    t_issue += PROF_T() - t1;
                 }
             }
-            if (prof && leader) { prof[0] = clock64() - t_begin; prof[1] = t_wait; prof[2] = t_issue; }
         }
     } else if (warp <= W) {
         // ------------------------------ MMA issuers (W warps) ------------------------------
@@ -273,41 +188,23 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_co
         const int instrs = p.row_bytes >> 5;                   // 32 bytes of K per instruction (16 bf16 / 8 tf32)
         const uint64_t desc_hi = make_kmajor_desc(0, p.row_bytes);          // everything but the start address
         const uint32_t rshift16 = static_cast<uint32_t>(p.rshift_bytes) >> 4;
+        const uint32_t btap16 = static_cast<uint32_t>(b_tap_bytes) >> 4;
         const int per_tile = p.k_iters / W;                    // stages this warp consumes per tile
         int s = w;                                             // ring slot of this warp's next stage
         uint32_t ph = 0, lt = 0;
         while (s >= p.stages) { s -= p.stages; ph ^= 1; }
-        // B tile of K step `it`: streamed = behind the A tile of the ring stage; resident = tile (n_tile, it) of the
-        // weight block.  In mode 3 the three vertical taps of a stage are 3*kchunks K steps apart.
-        const uint32_t btap16 = static_cast<uint32_t>(p.b_resident ? 3 * p.kchunks * b_tap_bytes : b_tap_bytes) >> 4;
-        long long* prof = (p.prof && blockIdx.x == 0) ? p.prof + 8 * (1 + w) : nullptr;
-        long long t_acc = 0, t_full = 0, t_issue = 0;
-        const long long t_begin = PROF_T();
-        if (p.b_resident) mbar_wait_warp(bfull_a, 0, leader);
-        const long long t_bres = PROF_T();
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const uint32_t buf = lt & 1, use = lt >> 1;
-            const long long ta0 = PROF_T();
-            mbar_wait_warp(acce_a + buf * 8, (use & 1) ^ 1, leader);
+            mbar_wait_a(acce_a + buf * 8, (use & 1) ^ 1);
             tc_fence_after();
-            t_acc += PROF_T() - ta0;
             const uint32_t tacc = tmem_base + (buf * W + w) * BN;
-            uint32_t b_step = 0;
-            if (p.b_resident) {
-                const int n_tile = t % n_tiles;
-                b_step = b_res_a + (n_tile * p.ksteps + w) * b_tap_bytes;
-            }
             for (int j = 0; j < per_tile; ++j) {
                 const uint32_t stage_a = smem_a + s * stage_bytes;
-                const long long tf0 = PROF_T();
-                mbar_wait_warp(full_a + s * 8, ph, leader);
+                mbar_wait_a(full_a + s * 8, ph);
                 tc_fence_after();
-                const long long tf1 = PROF_T();
-                t_full += tf1 - tf0;
                 if (leader) {
-                    const uint32_t b_addr = p.b_resident ? b_step : stage_a + a_bytes;
                     const uint64_t da = desc_hi | static_cast<uint64_t>((stage_a & 0x3FFFFu) >> 4);
-                    const uint64_t db = desc_hi | static_cast<uint64_t>((b_addr & 0x3FFFFu) >> 4);
+                    const uint64_t db = desc_hi | static_cast<uint64_t>(((stage_a + a_bytes) & 0x3FFFFu) >> 4);
                     for (int r = 0; r < taps; ++r)
                         for (int k = 0; k < instrs; ++k)
                             umma<kTf32>(tacc, da + r * rshift16 + 2 * k, db + r * btap16 + 2 * k, idesc,
@@ -316,106 +213,48 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_co
                     if (j == per_tile - 1) umma_commit_a(accf_a + buf * 8);
                 }
                 __syncwarp();
-                t_issue += PROF_T() - tf1;
-                b_step += W * b_tap_bytes;
                 s += W;
                 while (s >= p.stages) { s -= p.stages; ph ^= 1; }
             }
         }
-        if (prof && leader) {
-            prof[0] = clock64() - t_begin; prof[1] = t_acc; prof[2] = t_full; prof[3] = t_issue; prof[4] = t_bres - t_begin;
-        }
-    } else if (warp > W + 4 * kEG) {
-        // ------------------------------ B-operand TMA producers (streaming weights) ------------------------------
-        // producer b issues the taps r = b, b+PB, ... of every stage (mode 3) or the single B box (b == 0); the A
-        // producer's expect_tx covers the bytes, the empty barrier of the slot gates both.
-        const int b = warp - (W + 4 * kEG + 1);
-        const bool leader = elect_one_sync();
-        if (!p.b_resident) {
-            int s = 0;
-            uint32_t ph = 0;
-            uint32_t stage_a = smem_a, fb = full_a, eb = empty_a;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int m_tile = t / n_tiles, n_tile = t - m_tile * n_tiles;
-                const int nb0 = n_tile * BN;
-                int tap_s = 0, kc = 0, bk = 0;
-                for (int it = 0; it < p.k_iters; ++it) {
-                    mbar_wait_warp(eb, ph ^ 1, leader);
-                    if (leader) {
-                        if (p.mode == 3) {
-                            const int col = tap_s * p.cin + kc;
-                            for (int r = b; r < 3; r += p.b_producers)
-                                tma_load_2d_a(stage_a + a_bytes + r * b_tap_bytes, &tmB, fb, col + 3 * r * p.cin, nb0);
-                        } else if (b == 0) {
-                            tma_load_2d_a(stage_a + a_bytes, &tmB, fb, bk, nb0);
-                        }
-                    }
-                    bk += p.kc;
-                    kc += p.kc;
-                    if (kc == p.kwrap) { kc = 0; ++tap_s; }
-                    stage_a += stage_bytes; fb += 8; eb += 8;
-                    if (++s == p.stages) { s = 0; ph ^= 1; stage_a = smem_a; fb = full_a; eb = empty_a; }
-                }
-            }
-        }
     } else {
-        // ------------------------------ epilogue ------------------------------
-        // kEG groups of 4 warps (one warp per TMEM lane quarter).  Group g handles the CTA's local tiles lt = g,
-        // g + kEG, ...; with two groups, group g always drains TMEM buffer g, so two tiles are in their epilogue at once
-        // (the epilogue -- drain, column statistics, coalesced stores -- is a ~4000-cycle latency chain per tile and
-        // was the bound of the narrow convolutions: profiles/conv_roles_r1.txt).
-        const int ew = warp - 1 - W;            // 0 .. 4*kEG-1
-        const int grp_id = ew >> 2;
+        // ------------------------------ epilogue (4 warps after the MMA warps) ------------------------------
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;          // row of the tile == output pixel
-        const int et = (ew & 3) * 32 + lane;    // 0..127 inside the group
-        uint8_t* my_tile = epi_tile + grp_id * (kTileM * kPitch);
-        float* my_cta_stats = cta_stats + grp_id * cta_stats_floats;
-        long long* prof = (p.prof && blockIdx.x == 0 && et == 0) ? p.prof + 8 * (5 + grp_id) : nullptr;
-        long long t_accw = 0, t_drain = 0, t_stats = 0, t_store = 0;
-        const long long t_begin = PROF_T();
-        // running column sums of this lane's columns (register path of the fused BN statistics): the grid is a multiple
-        // of n_tiles, so every tile of this CTA has the same n_tile and a lane always owns the same columns
-        float run_s[BN / 16], run_q[BN / 16];
-#pragma unroll
-        for (int i = 0; i < BN / 16; ++i) { run_s[i] = 0.f; run_q[i] = 0.f; }
-        const bool reg_stats = kEpi == EPI_RAW_STATS && fused_bn && p.stats == nullptr;
-        uint32_t lt = grp_id;
-        for (int t = blockIdx.x + grp_id * gridDim.x; t < total_tiles; t += kEG * gridDim.x, lt += kEG) {
-            const int m_tile = t / n_tiles, n_tile = t - m_tile * n_tiles;
+        const int et = (warp - 1 - W) * 32 + lane;  // 0..127 epilogue thread id
+        uint32_t lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int m_tile = t / n_tiles, n_tile = t % n_tiles;
             const uint32_t buf = lt & 1, use = lt >> 1;
             const int m0 = m_tile * kTileM, c_base = n_tile * BN;
             const int valid_rows = min(kTileM, p.M - m0);
-            const long long te0 = PROF_T();
-            mbar_wait_warp(accf_a + buf * 8, use & 1, lane == 0);
+            mbar_wait_a(accf_a + buf * 8, use & 1);
             tc_fence_after();
-            const long long te1 = PROF_T();
-            t_accw += te1 - te0;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * W * BN;
 
             if constexpr (kEpi == EPI_F32_BIAS) {
                 float* out = reinterpret_cast<float*>(p.out);
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + c0, v);
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
                     for (int ww = 1; ww < W; ++ww) {            // add the other MMA warps' partial accumulators
-                        uint32_t u[16];
-                        tmem_ld16(taddr + ww * BN + c0, u);
+                        uint32_t u[32];
+                        tmem_ld32(taddr + ww * BN + c0, u);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
                     }
-                    if (c0 + 16 >= BN) {                        // accumulator fully read: hand it back to the MMA warps
+                    if (c0 + 32 >= BN) {                        // accumulator fully read: hand it back to the MMA warps
                         tc_fence_before();
                         mbar_arrive_a(acce_a + buf * 8);
                     }
                     if (row < valid_rows) {
                         float* dst = out + static_cast<size_t>(m0 + row) * p.ldo + c_base + c0;
-                        if (c_base + c0 + 16 <= p.N) {
+                        if (c_base + c0 + 32 <= p.N) {
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
+                            for (int j = 0; j < 32; j += 4) {
                                 float4 o;
                                 o.x = __uint_as_float(v[j + 0]) + (p.bias ? p.bias[c_base + c0 + j + 0] : 0.f);
                                 o.y = __uint_as_float(v[j + 1]) + (p.bias ? p.bias[c_base + c0 + j + 1] : 0.f);
@@ -425,194 +264,130 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_co
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
+                            for (int j = 0; j < 32; ++j)
                                 if (c_base + c0 + j < p.N)
                                     dst[j] = __uint_as_float(v[j]) + (p.bias ? p.bias[c_base + c0 + j] : 0.f);
                         }
                     }
                 }
             } else {
-                // previous tile's readers of this group's staging buffer must be done before it is overwritten
-                epi_group_barrier(grp_id);
-#pragma unroll
-                for (int c0 = 0; c0 < BN; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + c0, v);
-                    if (W == 1) {
+                // previous tile's readers of the staging buffer must be done before it is overwritten
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+                    for (int ww = 1; ww < W; ++ww) {
+                        uint32_t u[32];
+                        tmem_ld32(taddr + ww * BN + c0, u);
                         tmem_ld_wait();
-                    } else {                                    // add the other MMA warps' partial accumulators
-                        uint32_t u[16];
-                        tmem_ld16(taddr + BN + c0, u);
-                        tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-                        if (W == 3) {
-                            tmem_ld16(taddr + 2 * BN + c0, u);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
                     }
-                    if (c0 + 16 >= BN) {
+                    if (c0 + 32 >= BN) {
                         tc_fence_before();
                         mbar_arrive_a(acce_a + buf * 8);
                     }
-                    uint32_t pk[8];
+                    uint4* dst = reinterpret_cast<uint4*>(epi_tile + row * kPitch + c0 * 2);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                    uint4* dst = reinterpret_cast<uint4*>(my_tile + row * kPitch + c0 * 2);
-                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    if (reg_stats) {
-                        // statistics of the bf16-ROUNDED outputs (what the next layer will read), rows past M excluded
-                        float x[16];
-                        const bool live = row < valid_rows;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            x[2 * j] = live ? bf16_lo(pk[j]) : 0.f;
-                            x[2 * j + 1] = live ? bf16_hi(pk[j]) : 0.f;
-                        }
-                        const float cs = warp_colsum16(x, lane);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) x[j] *= x[j];
-                        const float cq = warp_colsum16(x, lane);
-                        run_s[c0 / 16] += cs;
-                        run_q[c0 / 16] += cq;
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                        o.y = pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                        o.z = pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                        o.w = pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                        dst[j] = o;
                     }
                 }
-                epi_group_barrier(grp_id);
-                const long long te2 = PROF_T();
-                t_drain += te2 - te1;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
                 // ---- per-tile column statistics from the bf16-rounded values ----
-                if (p.stats != nullptr) {
+                if (p.stats != nullptr || fused_bn) {
                     constexpr int kPairs = BN / 2;
                     constexpr int kGroups = 128 / kPairs;                   // BN=32:8, 64:4, 128:2
-                    constexpr int kRowsPer = kTileM / kGroups;              // rows each thread adds up
                     const int pair = et % kPairs, grp = et / kPairs;
                     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                    const uint8_t* src = my_tile + grp * kPitch + pair * 4;
-#pragma unroll 8
-                    for (int i = 0; i < kRowsPer; ++i) {
-                        if (grp + i * kGroups < valid_rows) {
-                            const uint32_t u = *reinterpret_cast<const uint32_t*>(src + i * kGroups * kPitch);
-                            const float a = bf16_lo(u), b = bf16_hi(u);
-                            s0 += a; s1 += b; q0 += a * a; q1 += b * b;
-                        }
+                    for (int r = grp; r < valid_rows; r += kGroups) {
+                        const uint32_t u = *reinterpret_cast<const uint32_t*>(epi_tile + r * kPitch + pair * 4);
+                        const float a = bf16_lo(u), b = bf16_hi(u);
+                        s0 += a; s1 += b; q0 += a * a; q1 += b * b;
                     }
-                    red_smem[grp_id][0][grp][pair * 2 + 0] = s0; red_smem[grp_id][0][grp][pair * 2 + 1] = s1;
-                    red_smem[grp_id][1][grp][pair * 2 + 0] = q0; red_smem[grp_id][1][grp][pair * 2 + 1] = q1;
-                    epi_group_barrier(grp_id);
+                    red_smem[0][grp][pair * 2 + 0] = s0; red_smem[0][grp][pair * 2 + 1] = s1;
+                    red_smem[1][grp][pair * 2 + 0] = q0; red_smem[1][grp][pair * 2 + 1] = q1;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (et < BN) {
-                        float sm = 0.f, qq = 0.f;
+                        float s = 0.f, qq = 0.f;
 #pragma unroll
-                        for (int gg = 0; gg < kGroups; ++gg) { sm += red_smem[grp_id][0][gg][et]; qq += red_smem[grp_id][1][gg][et]; }
+                        for (int gg = 0; gg < kGroups; ++gg) { s += red_smem[0][gg][et]; qq += red_smem[1][gg][et]; }
                         if (p.stats != nullptr) {
                             float* st = p.stats + static_cast<size_t>(m_tile) * 2 * p.N;
-                            st[c_base + et] = sm;
+                            st[c_base + et] = s;
                             st[p.N + c_base + et] = qq;
                         }
-                        if (fused_bn) {                          // owner thread of this column inside the group: no race
-                            my_cta_stats[c_base + et] += sm;
-                            my_cta_stats[p.N + c_base + et] += qq;
+                        if (fused_bn) {                          // owner thread of this column: no race
+                            cta_stats[c_base + et] += s;
+                            cta_stats[p.N + c_base + et] += qq;
                         }
                     }
                 }
-                const long long te3 = PROF_T();
-                t_stats += te3 - te2;
                 // ---- coalesced 16-byte stores of the tile ----
                 __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
                 constexpr int kChunksPerRow = BN / 8;
-#pragma unroll 4
                 for (int ch = et; ch < kTileM * kChunksPerRow; ch += 128) {
                     const int r = ch / kChunksPerRow, cc = ch % kChunksPerRow;
                     if (r < valid_rows) {
-                        const uint4 o = *reinterpret_cast<const uint4*>(my_tile + r * kPitch + cc * 16);
+                        const uint4 o = *reinterpret_cast<const uint4*>(epi_tile + r * kPitch + cc * 16);
                         *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + r) * p.ldo + c_base + cc * 8) = o;
                     }
                 }
-                t_store += PROF_T() - te3;
             }
-        }
-        if (prof) {
-            prof[0] = clock64() - t_begin; prof[1] = t_accw; prof[2] = t_drain; prof[3] = t_stats; prof[4] = t_store;
-            prof[5] = lt;
         }
         if constexpr (kEpi == EPI_RAW_STATS) {
             if (fused_bn) {
                 __shared__ int s_is_last;
-                epi_group_barrier(grp_id);
-                if (reg_stats) {
-                    // lane pairs hold the column totals of this warp's 32 rows: park them per warp, add the four warps
-                    const int col_of_lane = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    float* part = my_cta_stats;                  // [4 warps][2][BN]
-                    if ((lane & 1) == 0) {
-#pragma unroll
-                        for (int i = 0; i < BN / 16; ++i) {
-                            part[((ew & 3) * 2 + 0) * BN + i * 16 + col_of_lane] = run_s[i];
-                            part[((ew & 3) * 2 + 1) * BN + i * 16 + col_of_lane] = run_q[i];
-                        }
-                    }
-                    epi_group_barrier(grp_id);
-                    const int c_fixed = (blockIdx.x % n_tiles) * BN;     // n_tile of every tile of this CTA
-                    for (int c = et; c < 2 * BN; c += 128) {
-                        const int which = c / BN, col = c - which * BN;
-                        const float v = part[(0 * 2 + which) * BN + col] + part[(1 * 2 + which) * BN + col] +
-                                        part[(2 * 2 + which) * BN + col] + part[(3 * 2 + which) * BN + col];
-                        if (v != 0.f && c_fixed + col < p.N) atomicAdd(p.bn_acc + which * p.N + c_fixed + col, static_cast<double>(v));
-                    }
-                } else {
-                    for (int c = et; c < 2 * p.N; c += 128) {
-                        const float v = my_cta_stats[c];
-                        if (v != 0.f) atomicAdd(p.bn_acc + c, static_cast<double>(v));
-                    }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = et; c < 2 * p.N; c += 128) {
+                    const float v = cta_stats[c];
+                    if (v != 0.f) atomicAdd(p.bn_acc + c, static_cast<double>(v));
                 }
                 __threadfence();
-                asm volatile("bar.sync 3, %0;" ::"n"(128 * kEG) : "memory");     // every epilogue group has flushed
-                if (grp_id == 0) {
-                    if (et == 0) {
-                        const unsigned prev = atomicAdd(p.bn_counter, 1u);
-                        s_is_last = prev == gridDim.x - 1;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    const unsigned prev = atomicAdd(p.bn_counter, 1u);
+                    s_is_last = prev == gridDim.x - 1;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (s_is_last) {
+                    __threadfence();
+                    for (int ch = et; ch < p.N; ch += 128) {
+                        const double sum = __ldcg(p.bn_acc + ch), sq = __ldcg(p.bn_acc + p.N + ch);
+                        const double mean = sum * p.inv_count;
+                        double var = sq * p.inv_count - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        const int pc = ch - p.c_lo;
+                        const float g = (p.gamma && pc >= 0) ? p.gamma[pc] : 1.f;
+                        const float b = (p.beta && pc >= 0) ? p.beta[pc] : 0.f;
+                        const float sc = g * rsqrtf(static_cast<float>(var) + p.eps);
+                        p.scale[ch] = sc;
+                        p.shift[ch] = b - static_cast<float>(mean) * sc;
+                        if (p.running_mean && pc >= 0)
+                            p.running_mean[pc] = (1.f - p.momentum) * p.running_mean[pc] + p.momentum * static_cast<float>(mean);
+                        if (p.running_var && pc >= 0)
+                            p.running_var[pc] = (1.f - p.momentum) * p.running_var[pc] +
+                                                p.momentum * static_cast<float>(var * p.unbias);
+                        p.bn_acc[ch] = 0.0;
+                        p.bn_acc[p.N + ch] = 0.0;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (s_is_last) {
-                        __threadfence();
-                        for (int ch = et; ch < p.N; ch += 128) {
-                            const double sum = __ldcg(p.bn_acc + ch), sq = __ldcg(p.bn_acc + p.N + ch);
-                            const double mean = sum * p.inv_count;
-                            double var = sq * p.inv_count - mean * mean;
-                            if (var < 0.0) var = 0.0;
-                            const int pc = ch - p.c_lo;
-                            const float g = (p.gamma && pc >= 0) ? p.gamma[pc] : 1.f;
-                            const float b = (p.beta && pc >= 0) ? p.beta[pc] : 0.f;
-                            const float sc = g * rsqrtf(static_cast<float>(var) + p.eps);
-                            p.scale[ch] = sc;
-                            p.shift[ch] = b - static_cast<float>(mean) * sc;
-                            if (p.running_mean && pc >= 0)
-                                p.running_mean[pc] = (1.f - p.momentum) * p.running_mean[pc] + p.momentum * static_cast<float>(mean);
-                            if (p.running_var && pc >= 0)
-                                p.running_var[pc] = (1.f - p.momentum) * p.running_var[pc] +
-                                                    p.momentum * static_cast<float>(var * p.unbias);
-                            p.bn_acc[ch] = 0.0;
-                            p.bn_acc[p.N + ch] = 0.0;
-                        }
-                        if (et == 0) *p.bn_counter = 0u;
-                    }
+                    if (et == 0) *p.bn_counter = 0u;
                 }
             }
         }
         tc_fence_before();
     }
-    if (p.prof && threadIdx.x == 0 && blockIdx.x == 0) p.prof[15 * 8 + 1] = clock64() - t_entry;   // producer done
     __syncthreads();
-    if (p.prof && threadIdx.x == 0 && blockIdx.x == 0) p.prof[15 * 8 + 2] = clock64() - t_entry;   // all roles done
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_n(tmem_base, p.tmem_cols);
-    }
-    if (p.prof && threadIdx.x == 0 && blockIdx.x < 600) {
-        unsigned long long ns;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-        p.prof[128 + blockIdx.x * 4 + 1] = static_cast<long long>(ns);
     }
 }
 
@@ -621,42 +396,27 @@ __global__ void __launch_bounds__(kMaxThreads, 2) tc_gemm_kernel(const __grid_co
 // ----------------------------------------------------------------------------------------------
 template <int BN, bool kTf32, int kEpi>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    const int stage_bytes = (p.a_rows + (p.b_resident ? 0 : (p.mode == 3 ? 3 : 1) * BN)) * p.row_bytes;
-    constexpr int kEG = BN <= 64 ? 2 : 1;
+    const int stage_bytes = (p.a_rows + (p.mode == 3 ? 3 : 1) * BN) * p.row_bytes;
     const size_t epi = kEpi == EPI_RAW_STATS
-                           ? kEG * (static_cast<size_t>(kTileM) * (BN * 2 + 16) +
-                                    (p.bn_acc ? sizeof(float) * (2 * p.N > 8 * BN ? 2 * p.N : 8 * BN) : 0))
+                           ? static_cast<size_t>(kTileM) * (BN * 2 + 16) + (p.bn_acc ? 2 * sizeof(float) * p.N : 0)
                            : 0;
-    const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + p.b_res_bytes + epi + 1024;
+    const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + epi + 1024;
+    BPB_CHECK(smem <= 200 * 1024, "tc_gemm: %zu bytes of shared memory requested", smem);
     auto kern = tc_gemm_kernel<BN, kTf32, kEpi>;
-    static int regs_per_thread = 0;
-    static size_t max_dyn_smem = 0, static_smem = 0;
-    if (regs_per_thread == 0) {
-        cudaFuncAttributes fa;
-        BPB_CUDA(cudaFuncGetAttributes(&fa, kern));
-        static_smem = fa.sharedSizeBytes;
-        max_dyn_smem = 227 * 1024 - fa.sharedSizeBytes;         // 227 KB per CTA minus the kernel's static part
-        BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn_smem));
-        regs_per_thread = fa.numRegs > 0 ? fa.numRegs : 64;
+    static bool configured = false;
+    if (!configured) {
+        BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
     }
-    BPB_CHECK(smem <= max_dyn_smem, "tc_gemm: %zu bytes of shared memory requested (max %zu)", smem, max_dyn_smem);
     const int total = ((p.M + kTileM - 1) / kTileM) * ((p.N + BN - 1) / BN);
     // persistent: exactly as many CTAs as are co-resident (registers / smem via the occupancy API, TMEM: 2*BN
     // columns each) -- a static tile assignment must never have a second wave of CTAs
     // (shared memory is the binding limit: 56 registers x 192 threads allow 6 CTAs; the occupancy API under-reports
     //  here, so the bound is computed directly: 227 KB usable per SM, ~4 KB static + reserved per CTA)
-    // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for configurations the hardware demonstrably runs two
-    //  of per SM -- CTA timeline in profiles/conv_roles_r1.txt -- so the bound is computed directly: 227 KB usable per
-    //  SM, 1 KB reserved per CTA, plus the kernel's static shared memory)
-    int per_sm = static_cast<int>((227 * 1024) / (smem + static_smem + 1024));
+    int per_sm = static_cast<int>((227 * 1024) / (smem + 4 * 1024));
     if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
-    const int threads = 32 * (1 + p.mma_warps + 4 * kEG + p.b_producers);
+    const int threads = 32 * (1 + p.mma_warps + 4);
     if (per_sm > 2048 / threads) per_sm = 2048 / threads;
-    {   // registers are allocated per warp in units of 256, warps in groups of 4
-        const int warps = ((threads / 32 + 3) / 4) * 4;
-        const int regs_cta = warps * (((regs_per_thread * 32) + 255) / 256) * 256;
-        if (per_sm > 65536 / regs_cta) per_sm = 65536 / regs_cta;
-    }
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     static int num_sms = 0;
@@ -667,8 +427,6 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     }
     int grid = num_sms * per_sm;
     if (grid > total) grid = total;
-    const int n_tiles_h = (p.N + BN - 1) / BN;
-    if (grid > n_tiles_h) grid -= grid % n_tiles_h;            // every CTA then keeps one n_tile (register BN statistics)
     kern<<<grid, threads, smem, stream>>>(tmA, tmB, p);
     BPB_LAUNCH_CHECK("tc_gemm_kernel");
     return 0;
@@ -690,42 +448,40 @@ static int pow2_cols(int c) {
 
 // Pick the number of MMA-issuing warps W (must divide k_iters), the TMEM allocation and the ring depth so that
 // (issuers per SM) = W x (CTAs per SM) is maximal: TMEM allows 512 / pow2(2*W*BN) CTAs, shared memory the rest.
-static bool choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_bytes, int b_res_bytes) {
+static void choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_bytes) {
     // The ring depth must be a multiple of W: then every ring slot is always consumed by the same MMA warp, which is
     // what the mbarrier parity protocol needs (a warp that shares a slot with another warp could skip a phase and
     // mistake an old completion for the one it is waiting for).
-    // b_res_bytes > 0: resident weights -- ring stages carry the A tile only and the weight block is a fixed cost.
-    const int stage_bytes = (p.a_rows + (b_res_bytes ? 0 : taps * bn_tile)) * p.row_bytes;
-    const int fixed = epi_bytes + b_res_bytes;
-    const int kMaxSmem = 212 * 1024;                       // + 1 KB alignment slack + <= 9.2 KB static  <= 227 KB
-    int best_w = 1, best_issuers = 0, best_stages = 0;
-    for (int w = kMaxMmaWarps; w >= 1; --w) {
-        if (p.k_iters % w) continue;
-        const int cols = pow2_cols(2 * w * bn_tile);
-        if (cols > 512) continue;
-        int ctas = 512 / cols;
-        if (ctas > 3) ctas = 3;
-        for (; ctas >= 1; --ctas) {
-            int budget = (227 * 1024) / ctas - 12 * 1024 - fixed;    // 12 KB: static smem (<= 9.2 KB) + reserved + alignment
-            if (budget > kMaxSmem - fixed) budget = kMaxSmem - fixed;
-            if (budget <= 0) continue;
-            int st = budget / stage_bytes;
-            if (st > 9) st = 9;
-            st = (st / w) * w;
-            int min_st = w < 2 ? 2 : w;
-            if (st < min_st) continue;
-            const int issuers = w * ctas;
-            if (issuers > best_issuers) { best_issuers = issuers; best_w = w; best_stages = st; }
-            break;
+    const int stage_bytes = (p.a_rows + taps * bn_tile) * p.row_bytes;
+    const int kMaxSmem = 190 * 1024;
+    int best_w = 1, best_issuers = 0, best_stages = 2;
+    // first pass: every MMA warp gets two ring slots (prefetch distance); second pass: one slot each
+    // (a first pass that demanded two slots per warp was measured slower: it trades CTAs per SM for ring depth)
+    for (int slots_per_warp = 1; slots_per_warp >= 1 && best_issuers == 0; --slots_per_warp) {
+        for (int w = kMaxMmaWarps; w >= 1; --w) {
+            if (p.k_iters % w) continue;
+            const int cols = pow2_cols(2 * w * bn_tile);
+            if (cols > 512) continue;
+            int ctas = 512 / cols;
+            if (ctas > 3) ctas = 3;
+            for (; ctas >= 1; --ctas) {
+                int budget = (227 * 1024) / ctas - 5 * 1024 - epi_bytes;
+                if (budget > kMaxSmem - epi_bytes) budget = kMaxSmem - epi_bytes;
+                int st = budget / stage_bytes;
+                if (st > 9) st = 9;
+                st = (st / w) * w;
+                int min_st = slots_per_warp * w;
+                if (min_st < 2) min_st = 2;
+                if (st < min_st) continue;
+                const int issuers = w * ctas;
+                if (issuers > best_issuers) { best_issuers = issuers; best_w = w; best_stages = st; }
+                break;
+            }
         }
     }
-    if (best_issuers == 0) return false;
     p.mma_warps = best_w;
     p.tmem_cols = pow2_cols(2 * best_w * bn_tile);
     p.stages = best_stages;
-    p.b_resident = b_res_bytes > 0;
-    p.b_res_bytes = b_res_bytes;
-    return true;
 }
 
 static int pick_bn(int m_tiles, int cout, int bn_hint) {
@@ -750,14 +506,13 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     BPB_CHECK(bnimg * wo * bh == 128, "conv_bf16_tc: tile does not cover 128 pixels (ho=%d wo=%d)", ho, wo);
     // row-shift mode: 3x3 stride-1, tile inside one image, vertical tap offset = whole swizzle atoms (Wo % 8 == 0)
     const bool rowshift = ksize == 3 && stride == 1 && bnimg == 1 && (wo % 8) == 0 && (bn_hint & 0x100) == 0;
-    const bool allow_resident = (bn_hint & 0x200) == 0;       // test hook: force streamed weights
     bn_hint &= 0xFF;
     // One thread can issue a tcgen05.mma only every ~98 cycles (tools/micro/umma_rate.cu), far slower than the
     // 16/32-cycle math of the N=32/64 MMAs these narrow convolutions need, so MMA *issue* is the bound and the lever is
     // the number of issuing CTAs per SM: 64-byte operand rows keep the ring stages small enough for 2-3 CTAs per SM.
     // 64-byte rows for the row-shift schedule: smaller ring stages -> two issuing CTAs per SM (measured faster
     // than 128-byte rows with one CTA per SM: 15.3 vs 16.2 ms per step)
-    const int kc = cin < 64 ? 32 : 64;
+    const int kc = (rowshift || cin < 64) ? 32 : 64;
     BPB_CHECK(cin % kc == 0, "conv_bf16_tc: cin %d not a multiple of %d", cin, kc);
 
     GemmParams p{};
@@ -789,27 +544,10 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
         p.unbias = p.M > 1 ? static_cast<double>(p.M) / static_cast<double>(p.M - 1) : 1.0;
         p.c_lo = bn->c_lo;
     }
-    p.prof = g_prof;
     const int m_tiles = (p.M + kTileM - 1) / kTileM;
     int bn_tile = pick_bn(m_tiles, cout, bn_hint);
     if (bn_hint == 0 && ksize == 3 && bn_tile > 64) bn_tile = 64;       // narrow tiles + several issuers beat one N=128 issuer
-    {
-        const int taps = rowshift ? 3 : 1;
-        const int epi_bytes = (bn_tile <= 64 ? 2 : 1) *
-                              (kTileM * (bn_tile * 2 + 16) + (bn ? 4 * (2 * cout > 8 * bn_tile ? 2 * cout : 8 * bn_tile) : 0));
-        p.ksteps = ksize * ksize * p.kchunks;
-        const int n_tiles = (cout + bn_tile - 1) / bn_tile;
-        const int b_all = n_tiles * p.ksteps * bn_tile * p.row_bytes;   // the whole (tile-padded) weight matrix
-        bool ok = false;
-        if (allow_resident && b_all <= 160 * 1024) ok = choose_issue_config(p, bn_tile, taps, epi_bytes, b_all);
-        if (!ok) {
-            ok = choose_issue_config(p, bn_tile, taps, epi_bytes, 0);
-            p.b_producers = taps;                                // streamed weights: one producer warp per B box of a stage
-            const int room = kMaxWarps - 1 - p.mma_warps - 4 * (bn_tile <= 64 ? 2 : 1);
-            if (p.b_producers > room) p.b_producers = room;
-        }
-        BPB_CHECK(ok, "conv_bf16_tc: no shared-memory configuration for cin=%d cout=%d k=%d", cin, cout, ksize);
-    }
+    choose_issue_config(p, bn_tile, (rowshift ? 3 : 1), kTileM * (bn_tile * 2 + 16) + (bn ? 8 * cout : 0));
 
     const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tmA, tmB;
@@ -857,9 +595,7 @@ int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bia
     const int m_tiles = (m + kTileM - 1) / kTileM;
     int bn = n >= 128 ? 128 : (n >= 64 ? 64 : 32);
     while (bn > 32 && m_tiles * ((n + bn - 1) / bn) < 148) bn >>= 1;
-    p.ksteps = p.kchunks;
-    BPB_CHECK(choose_issue_config(p, bn, 1, 0, 0), "linear_tf32_tc: no shared-memory configuration");
-    p.b_producers = 1;
+    choose_issue_config(p, bn, 1, 0);
     CUtensorMap tmA, tmB;
     if (a_mode == 0) {
         BPB_CHECK(lda % 4 == 0 && lda >= k, "linear_tf32_tc: lda=%lld invalid", (long long)lda);

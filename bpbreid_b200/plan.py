@@ -14,6 +14,7 @@ pooled embeddings are group-major fp32 [K+3, N, C] = {global, foreground, backgr
 from __future__ import annotations
 
 import ctypes
+import os
 from contextlib import contextmanager
 
 import torch
@@ -62,7 +63,10 @@ class ForwardPlan:
         self.training = bool(training)
         self.device = device
         self.conv_impl = conv_impl
-        self.ops = []                 # (ctypes fn, args tuple) ; stream appended at run time
+        self.ops = []                 # (ctypes fn, args, name, lane) ; stream appended at run time; fn None = fork/join
+        self._lane = 0                # stream lane ops are being recorded on (0 = the caller's stream)
+        self._buf_lane = {}           # id(buffer) -> lane that owns it (buffers are only reused inside their lane)
+        self._side_streams = []
         self.setup_ops = []           # run once at build / after a weight refresh (eval-mode BN folds)
         self.keepalive = []           # ctypes arrays referenced by ops
         self.persistent = []          # tensors that must outlive the plan build
@@ -71,6 +75,7 @@ class ForwardPlan:
         self.launches = 0
         self.graph = None
         self.use_graph = use_graph
+        self.multi_stream = os.environ.get("BPB_SINGLE_STREAM", "0") != "1"
         self.lib = _lib.load()
         # debug: keep every intermediate activation alive (no buffer reuse) and record (block, inputs, outputs) so
         # tests can check each block of the real network against the oracle on the block's actual input
@@ -91,11 +96,12 @@ class ForwardPlan:
         for s in shape:
             numel *= s
         nbytes = numel * torch.empty((), dtype=dtype).element_size()
-        lst = self._free.get(nbytes)
+        lst = self._free.get((self._lane, nbytes))
         if lst:
             buf = lst.pop()
         else:
             buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._buf_lane[id(buf)] = self._lane
         self._scopes[-1].append(buf)
         return buf.view(dtype).view(*shape), buf
 
@@ -122,7 +128,7 @@ class ForwardPlan:
                 if self.debug or id(buf) in kept_ids:
                     self._scopes[-1].append(buf)
                 else:
-                    self._free.setdefault(buf.numel(), []).append(buf)
+                    self._free.setdefault((self._buf_lane[id(buf)], buf.numel()), []).append(buf)
 
     def _trace(self, kind, mods, ins, outs, **extra):
         if self.debug:
@@ -131,8 +137,28 @@ class ForwardPlan:
 
     # ------------------------------------------------------------------ op recording
     def _op(self, name, *args):
-        self.ops.append((getattr(self.lib, name), args, name))
+        self.ops.append((getattr(self.lib, name), args, name, self._lane))
         self.launches += 1
+
+    # ---- stream lanes: independent sub-graphs (HRNet branches, fuse outputs) are recorded on side streams so that
+    # ---- the small low-resolution layers overlap the big ones; buffers never migrate between lanes while live
+    @contextmanager
+    def lane(self, idx):
+        prev, self._lane = self._lane, (idx if self.multi_stream else 0)
+        try:
+            yield
+        finally:
+            self._lane = prev
+
+    def fork(self, lanes):
+        """side lanes start after everything recorded so far on lane 0"""
+        if self.multi_stream:
+            self.ops.append((None, tuple(l for l in lanes if l != 0), "fork", 0))
+
+    def join(self):
+        """lane 0 waits for every side lane forked since the last join"""
+        if self.multi_stream:
+            self.ops.append((None, (), "join", 0))
 
     def _setup_op(self, name, *args):
         self.setup_ops.append((getattr(self.lib, name), args, name))
@@ -338,31 +364,39 @@ class ForwardPlan:
     def hr_module(self, xs, mod):
         nb = len(xs)
         with self.scope() as keep:
+            # branch b runs on stream lane b (independent until the fuse layer, hrnet.py:259-279)
             ys = []
+            self.fork(range(1, nb))
             for b in range(nb):
-                t = xs[b]
-                for blk in mod.branches[b]:
-                    t = self.basic_block(t, blk)
-                ys.append(t)
+                with self.lane(b):
+                    t = xs[b]
+                    for blk in mod.branches[b]:
+                        t = self.basic_block(t, blk)
+                    ys.append(t)
+            self.join()
+            # fuse output i (needs every branch) on lane i
             outs = []
+            self.fork(range(1, nb))
             for i in range(nb):
-                terms = []
-                for j in range(nb):
-                    if j == i:
-                        terms.append((ys[j], 0))
-                    elif j > i:
-                        f = mod.fuse_layers[i][j]
-                        terms.append((self.conv_bn(ys[j], f[0], f[1]), j - i))
-                    else:
-                        t = ys[j]
-                        chain = mod.fuse_layers[i][j]
-                        for k, st in enumerate(chain):
-                            lz = self.conv_bn(t, st[0], st[1])
-                            if k == len(chain) - 1:
-                                terms.append((lz, 0))
-                            else:
-                                t = self.apply(lz, True)
-                outs.append(self.fuse(terms, ys[i]))
+                with self.lane(i):
+                    terms = []
+                    for j in range(nb):
+                        if j == i:
+                            terms.append((ys[j], 0))
+                        elif j > i:
+                            f = mod.fuse_layers[i][j]
+                            terms.append((self.conv_bn(ys[j], f[0], f[1]), j - i))
+                        else:
+                            t = ys[j]
+                            chain = mod.fuse_layers[i][j]
+                            for k, st in enumerate(chain):
+                                lz = self.conv_bn(t, st[0], st[1])
+                                if k == len(chain) - 1:
+                                    terms.append((lz, 0))
+                                else:
+                                    t = self.apply(lz, True)
+                    outs.append(self.fuse(terms, ys[i]))
+            self.join()
             keep.extend(outs)
         self._trace("fuse", mod, ys, outs)
         return outs
@@ -385,7 +419,12 @@ class ForwardPlan:
             xs = xs + [self.conv_bn_relu(xs[-1], t[0], t[1])]
             for mod in bb.stage4:
                 xs = self.hr_module(xs, mod)
-            br = [self.bottleneck(xs[i], bb.incre_modules[i][0]) for i in range(4)]
+            br = []
+            self.fork(range(1, 4))
+            for i in range(4):
+                with self.lane(i):
+                    br.append(self.bottleneck(xs[i], bb.incre_modules[i][0]))
+            self.join()
             keep.extend(br)
         return br
 
@@ -600,12 +639,34 @@ class ForwardPlan:
         if self._need_setup:
             self._run_list(self.setup_ops)
             self._need_setup = False
-        stream = torch.cuda.current_stream().cuda_stream
+        main = torch.cuda.current_stream()
+        nside = max((op[3] for op in self.ops), default=0)
+        while len(self._side_streams) < nside:
+            self._side_streams.append(torch.cuda.Stream(device=self.device))
+        streams = [main] + self._side_streams
+        ptrs = [st.cuda_stream for st in streams]
+        active = []
         err = self.lib.bpb_last_error
-        for fn, args, name in self.ops:
-            rc = fn(*args, stream)
+        for fn, args, name, lane in self.ops:
+            if fn is None:
+                if name == "fork":
+                    for l in args:
+                        if l not in active:
+                            streams[l].wait_stream(main)
+                            active.append(l)
+                else:
+                    for l in active:
+                        main.wait_stream(streams[l])
+                    active = []
+                continue
+            if lane != 0 and lane not in active:             # op on a lane nobody forked: order it after lane 0
+                streams[lane].wait_stream(main)
+                active.append(lane)
+            rc = fn(*args, ptrs[lane])
             if rc != 0:
                 raise RuntimeError(f"{name} failed (rc={rc}): {err().decode()}")
+        for l in active:
+            main.wait_stream(streams[l])
 
     def run(self, images):
         self.images.copy_(images, non_blocking=True)

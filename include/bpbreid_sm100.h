@@ -32,9 +32,6 @@ int bpb_abi_version(void);
 int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                   int ksize, int stride, int bn_hint, void* stream);
 int bpb_conv_num_mtiles(int n, int ho, int wo);
-/* Diagnostic hook (tools/probe_conv.py): device buffer [16][8] int64 that CTA 0 of the following bpb_conv_* launches
- * fills with per-role cycle counters (producer / MMA warps / epilogue); NULL switches it off (default). */
-int bpb_conv_set_profile_buffer(void* buf);
 /* Same convolution with the train-mode BatchNorm that follows it fused into the launch (conv + nn.BatchNorm2d call
  * pairs, e.g. hrnet.py:82-83): every CTA adds its per-channel sums to `bn_workspace` (fp64 atomics) and the last CTA
  * turns them into scale/shift [cout] (biased batch variance), updates running_mean/var like nn.BatchNorm2d and

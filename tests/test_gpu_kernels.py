@@ -127,28 +127,6 @@ def test_conv_fused_bn_matches_two_pass_statistics():
     assert int(ws.count_nonzero()) == 0
 
 
-@pytest.mark.parametrize("shape", [(4, 64, 32, 32, 32, 3, 1), (4, 32, 16, 64, 64, 3, 1), (4, 64, 32, 64, 256, 1, 1),
-                                   (4, 64, 32, 32, 32, 3, 2), (4, 64, 32, 256, 64, 1, 1), (2, 64, 32, 256, 32, 3, 1)])
-@pytest.mark.parametrize("hint", [0x200, 0x300])
-def test_conv_streamed_weights_equal_resident_weights(shape, hint):
-    """Layers whose whole weight matrix fits in shared memory keep it resident (loaded once per CTA); bn_hint bit 9
-    forces the streamed schedule (weights ride the ring with their own TMA producer warps).  Same MMAs, same order:
-    the outputs must be identical."""
-    n, h, w, cin, cout, k, s = shape
-    g = torch.Generator().manual_seed(23)
-    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).to(DEV)
-    wp = pack_w((torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5)).to(DEV)
-    pad = k // 2
-    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
-    ya = torch.full((n, ho, wo, cout), float("nan"), device=DEV, dtype=torch.bfloat16)
-    yb = torch.full_like(ya, float("nan"))
-    _lib.call("bpb_conv_bf16", x.data_ptr(), wp.data_ptr(), ya.data_ptr(), None, n, h, w, cin, cout, k, s, hint & 0x100, S())
-    _lib.call("bpb_conv_bf16", x.data_ptr(), wp.data_ptr(), yb.data_ptr(), None, n, h, w, cin, cout, k, s, hint, S())
-    torch.cuda.synchronize()
-    assert torch.isfinite(ya.float()).all() and torch.isfinite(yb.float()).all()
-    assert torch.equal(ya, yb)
-
-
 def test_conv_bn_hint_variants():
     n, h, w, cin, cout, k, s = 4, 32, 16, 64, 128, 3, 1
     g = torch.Generator().manual_seed(3)

@@ -36,26 +36,3 @@ for (n, h, w, cin, cout, k, st) in SHAPES:
     flops = 2.0 * n * ho * wo * cout * k * k * cin
     byts = (n * h * w * cin + n * ho * wo * cout + cout * k * k * cin) * 2
     print(f"conv n{n} {h}x{w} {cin}->{cout} k{k} s{st}: {ms*1e3:8.1f} us  {flops/ms/1e9:8.1f} TFLOP/s  {byts/ms/1e6:8.1f} GB/s (algorithmic)")
-    if os.environ.get("BPB_CONV_ROLES"):
-        # per-role cycle counters of CTA 0 (diagnostic hook)
-        prof = torch.zeros(128 + 2400, dtype=torch.int64, device=dev)
-        _lib.call("bpb_conv_set_profile_buffer", prof.data_ptr())
-        call(); torch.cuda.synchronize()
-        _lib.call("bpb_conv_set_profile_buffer", None)
-        full = prof.cpu().numpy()
-        pr = full[:128].reshape(16, 8)
-        tl = full[128:].reshape(600, 4)
-        tl = tl[tl[:, 0] > 0]
-        if len(tl):
-            t0 = tl[:, 0].min()
-            st, en = tl[:, 0] - t0, tl[:, 1] - t0
-            per_sm = np.bincount(tl[:, 2].astype(int))
-            print(f"    kernel span {en.max()/1e3:.1f} us  CTAs {len(tl)}  SMs used {np.count_nonzero(per_sm)}  max CTAs/SM {per_sm.max()}  start ns [min {st.min()} med {int(np.median(st))} max {st.max()}]  end ns [min {en.min()} med {int(np.median(en))} max {en.max()}]")
-        print(f"    cta0 cycles: setup {pr[15,0]}  producer-done {pr[15,1]}  all-roles-done {pr[15,2]}")
-        print(f"    producer: total {pr[0,0]}  wait_empty {pr[0,1]}  issue {pr[0,2]}")
-        for wv in range(3):
-            if pr[1 + wv, 0]:
-                print(f"    mma{wv}: total {pr[1+wv,0]}  wait_acc_empty {pr[1+wv,1]}  wait_full {pr[1+wv,2]}  issue {pr[1+wv,3]}  wait_b_resident {pr[1+wv,4]}")
-        for gq in range(2):
-            if pr[5 + gq, 0]:
-                print(f"    epilogue{gq}: total {pr[5+gq,0]}  wait_acc_full {pr[5+gq,1]}  drain {pr[5+gq,2]}  stats {pr[5+gq,3]}  store {pr[5+gq,4]}  lt {pr[5+gq,5]}")
