@@ -40,38 +40,83 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
 // (1) per-image partial BN statistics of the (virtually) upsampled branch: partial[n][2][ctot] at channel c_off
 //     grid (N, Cb/64), block 256 = 8 channel-vectors x 32 pixel lanes
 // ----------------------------------------------------------------------------------------------
+// The variance term is quadratic in the branch values, but the bilinear operator is separable, U = Uy (x) Ux, so
+//   sum_hi (U x)^2 = x^T (Ty (x) Tx) x,   Ty = Uy^T Uy, Tx = Ux^T Ux  (tridiagonal: an output row touches <= 2 input rows)
+// i.e. a 3x3 stencil at LOW resolution (9 MACs per low-res value instead of 5 flops per HIGH-res value: 8-32x fewer
+// for the stride-8/16/32 branches); the mean term uses the column sums of Uy and Ux.
 __global__ void __launch_bounds__(256) branch_stats_kernel(const uint4* __restrict__ x, int hb, int wb, int cb, int h,
                                                            int w, float* __restrict__ partial, int c_off, int ctot) {
     extern __shared__ uint4 slab[];                     // [hb*wb][8] vectors (64 channels) -- unused when hb == h
+    __shared__ float coef[6][64];                       // y: colsum, diag, offdiag(i,i+1) ; x: the same
     const int n = blockIdx.x, sl = blockIdx.y;
     const int cv = threadIdx.x & 7, pl = threadIdx.x >> 3;
     const int cvec = cb / 8;
     const uint4* base = x + static_cast<int64_t>(n) * hb * wb * cvec + sl * 8;
     const bool direct = (hb == h && wb == w);
-    if (!direct) {
-        for (int i = threadIdx.x; i < hb * wb * 8; i += 256) slab[i] = base[static_cast<int64_t>(i >> 3) * cvec + (i & 7)];
-        __syncthreads();
-    }
     float s[8], q[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) { s[t] = 0.f; q[t] = 0.f; }
-    for (int p = pl; p < h * w; p += 32) {
-        float v[8];
-        if (direct) {
+    if (direct) {
+#pragma unroll 4
+        for (int p = pl; p < h * w; p += 32) {
+            float v[8];
             unpack8f(base[static_cast<int64_t>(p) * cvec + cv], v);
-        } else {
-            const Tap ty = make_tap(p / w, hb, h), tx = make_tap(p % w, wb, w);
-            float a[8], b[8], c[8], d[8];
-            unpack8f(slab[(ty.i0 * wb + tx.i0) * 8 + cv], a);
-            unpack8f(slab[(ty.i0 * wb + tx.i1) * 8 + cv], b);
-            unpack8f(slab[(ty.i1 * wb + tx.i0) * 8 + cv], c);
-            unpack8f(slab[(ty.i1 * wb + tx.i1) * 8 + cv], d);
 #pragma unroll
-            for (int t = 0; t < 8; ++t)
-                v[t] = (1.f - ty.l) * ((1.f - tx.l) * a[t] + tx.l * b[t]) + ty.l * ((1.f - tx.l) * c[t] + tx.l * d[t]);
+            for (int t = 0; t < 8; ++t) { s[t] += v[t]; q[t] += v[t] * v[t]; }
         }
+    } else {
+        for (int i = threadIdx.x; i < hb * wb * 8; i += 256) slab[i] = base[static_cast<int64_t>(i >> 3) * cvec + (i & 7)];
+        if (threadIdx.x < 2) {                          // thread 0: y axis, thread 1: x axis
+            const int in = threadIdx.x == 0 ? hb : wb, out = threadIdx.x == 0 ? h : w;
+            float* cs = coef[threadIdx.x * 3 + 0];
+            float* dg = coef[threadIdx.x * 3 + 1];
+            float* od = coef[threadIdx.x * 3 + 2];
+            for (int i = 0; i < in; ++i) { cs[i] = 0.f; dg[i] = 0.f; od[i] = 0.f; }
+            for (int o = 0; o < out; ++o) {
+                const Tap tp = make_tap(o, in, out);
+                const float a = 1.f - tp.l, b = tp.l;
+                if (tp.i1 == tp.i0) {                   // last input row: both taps coincide
+                    cs[tp.i0] += a + b; dg[tp.i0] += (a + b) * (a + b);
+                } else {
+                    cs[tp.i0] += a; cs[tp.i1] += b;
+                    dg[tp.i0] += a * a; dg[tp.i1] += b * b; od[tp.i0] += a * b;
+                }
+            }
+        }
+        __syncthreads();
+        const float* csy = coef[0]; const float* dgy = coef[1]; const float* ody = coef[2];
+        const float* csx = coef[3]; const float* dgx = coef[4]; const float* odx = coef[5];
+        for (int p = pl; p < hb * wb; p += 32) {
+            const int iy = p / wb, ix = p - iy * wb;
+            // stencil weights of the three rows / columns around (iy, ix); zero outside the map
+            const float wy[3] = {iy > 0 ? ody[iy - 1] : 0.f, dgy[iy], iy + 1 < hb ? ody[iy] : 0.f};
+            const float wx[3] = {ix > 0 ? odx[ix - 1] : 0.f, dgx[ix], ix + 1 < wb ? odx[ix] : 0.f};
+            float z[8], ctr[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { s[t] += v[t]; q[t] += v[t] * v[t]; }
+            for (int t = 0; t < 8; ++t) z[t] = 0.f;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = iy + dy;
+                if (yy < 0 || yy >= hb) continue;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = ix + dx;
+                    if (xx < 0 || xx >= wb) continue;
+                    float v[8];
+                    unpack8f(slab[(yy * wb + xx) * 8 + cv], v);
+                    const float wgt = wy[dy + 1] * wx[dx + 1];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) z[t] += wgt * v[t];
+                    if (dy == 0 && dx == 0) {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) ctr[t] = v[t];
+                    }
+                }
+            }
+            const float cw = csy[iy] * csx[ix];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { s[t] += cw * ctr[t]; q[t] += ctr[t] * z[t]; }
+        }
     }
     __shared__ float red[2][32][64];
 #pragma unroll
@@ -92,6 +137,7 @@ int head_branch_stats(const void* x, int n, int hb, int wb, int cb, int h, int w
     const bool direct = hb == h && wb == w;
     const size_t smem = direct ? 0 : static_cast<size_t>(hb) * wb * 8 * sizeof(uint4);
     BPB_CHECK(smem <= 160 * 1024, "head_branch_stats: branch map %dx%d too large for shared memory", hb, wb);
+    BPB_CHECK(direct || (hb <= 64 && wb <= 64), "head_branch_stats: low-resolution branch %dx%d larger than 64", hb, wb);
     static bool configured = false;
     if (!configured) {
         BPB_CUDA(cudaFuncSetAttribute(branch_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -356,7 +402,7 @@ __global__ void __launch_bounds__(128) branch_pool_kernel(const uint4* __restric
     extern __shared__ float wts[];                        // [q][J]
     const int im = blockIdx.x, slab = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cvec = cb / 8, cv = slab * 32 + lane;
+    const int cvec = cb / 8;
     const float* src = mt + static_cast<int64_t>(im) * J * q;
     for (int i = threadIdx.x; i < q * J; i += blockDim.x) {
         const int j = i / q, qq = i % q;
@@ -368,9 +414,33 @@ __global__ void __launch_bounds__(128) branch_pool_kernel(const uint4* __restric
     for (int j = 0; j < J; ++j)
 #pragma unroll
         for (int t = 0; t < 8; ++t) acc[j][t] = 0.f;
-    if (cv < cvec) {
-        const uint4* base = x + static_cast<int64_t>(im) * q * cvec + cv;
-        for (int p = warp; p < q; p += 4) {
+    // a slab narrower than 32 channel vectors (C = 128) lets the spare lanes take other pixels
+    int lpp = cvec - slab * 32 >= 32 ? 32 : cvec - slab * 32;         // lanes per pixel
+    if (lpp <= 0 || (32 % lpp) != 0) lpp = 32;
+    const int ppw = 32 / lpp;                                         // pixels per warp iteration
+    const int sub = lane / lpp, cl = lane - sub * lpp;
+    const int cvl = slab * 32 + cl;
+    if (cvl < cvec) {
+        const uint4* base = x + static_cast<int64_t>(im) * q * cvec + cvl;
+        const int step = 4 * ppw;
+        int p = warp * ppw + sub;
+        for (; p + 3 * step < q; p += 4 * step) {                     // four loads in flight
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = base[static_cast<int64_t>(p + k * step) * cvec];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float f[8];
+                unpack8f(u[k], f);
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const float wj = wts[(p + k * step) * J + j];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) acc[j][t] += wj * f[t];
+                }
+            }
+        }
+        for (; p < q; p += step) {
             float f[8];
             unpack8f(base[static_cast<int64_t>(p) * cvec], f);
 #pragma unroll
@@ -390,18 +460,19 @@ __global__ void __launch_bounds__(128) branch_pool_kernel(const uint4* __restric
 #pragma unroll
         for (int t = 0; t < 8; ++t) mine[j * 8 + t] = acc[j][t];
     __syncthreads();
-    if (warp == 0 && cv < cvec) {
+    if (warp == 0 && sub == 0 && cvl < cvec) {
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const float norm = j < 3 ? inv_hw : 1.f / fmaxf(mask_sum[im * J + j], 1e-6f);
             float o[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                float s = 0.f;
-                for (int wv = 0; wv < 4; ++wv) s += red[(wv * 32 + lane) * kPer + j * 8 + t];
-                o[t] = s * norm;
+                float sum = 0.f;
+                for (int wv = 0; wv < 4; ++wv)
+                    for (int sb = 0; sb < ppw; ++sb) sum += red[(wv * 32 + sb * lpp + cl) * kPer + j * 8 + t];
+                o[t] = sum * norm;
             }
-            float* dst = pooled + (static_cast<int64_t>(j) * n + im) * ctot + c_off + cv * 8;
+            float* dst = pooled + (static_cast<int64_t>(j) * n + im) * ctot + c_off + cvl * 8;
             *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }

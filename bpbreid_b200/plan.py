@@ -509,8 +509,12 @@ class ForwardPlan:
         scale, shift = self._small((ctot,)), self._small((ctot,))
         if self.training:
             partial = self._small((n, 2, ctot))
-            for b, off in zip(br, offs):
-                self._op("bpb_head_branch_stats", b.t.data_ptr(), n, b.h, b.w, b.c, h, w, partial.data_ptr(), off, ctot)
+            self.fork(range(1, len(br)))
+            for i, (b, off) in enumerate(zip(br, offs)):
+                with self.lane(i):
+                    self._op("bpb_head_branch_stats", b.t.data_ptr(), n, b.h, b.w, b.c, h, w, partial.data_ptr(), off,
+                             ctot)
+            self.join()
             bn = pc.bn
             mom = bn.momentum if bn.momentum is not None else 0.1
             self._op("bpb_bn_finalize", partial.data_ptr(), n, ctot, 0, n * h * w, bn.weight.data_ptr(),
@@ -526,12 +530,15 @@ class ForwardPlan:
              shift.data_ptr(), kp1, ctot, wf.data_ptr(), bf.data_ptr())
         self._alloc_head_outputs(h, w, ctot)
         lows, mts = [], []
-        for b, off in zip(br, offs):
+        self.fork(range(1, len(br)))
+        for i, (b, off) in enumerate(zip(br, offs)):
             lo = self._small((n * b.h * b.w, kp1))
-            self._op("bpb_head_lowres_logits", b.t.data_ptr(), wf.data_ptr(), n * b.h * b.w, b.c, off, ctot, kp1,
-                     lo.data_ptr())
+            with self.lane(i):
+                self._op("bpb_head_lowres_logits", b.t.data_ptr(), wf.data_ptr(), n * b.h * b.w, b.c, off, ctot, kp1,
+                         lo.data_ptr())
             lows.append(lo)
             mts.append(self._small((n, J, b.h * b.w)))
+        self.join()
         self.mask_sum = self._small((n, J))
         self._op("bpb_head_pixel", self._ptr_array(lows), self._ptr_array(mts), self._int_array([b.h for b in br]),
                  self._int_array([b.w for b in br]), len(br), bf.data_ptr(), n, h, w, kp1, self.logits.data_ptr(),
@@ -539,9 +546,12 @@ class ForwardPlan:
                  self.mask_sum.data_ptr())
         self._op("bpb_vis_unpack", self.vis_bits.data_ptr(), self.vis_cont.data_ptr(), n, kp1, self.vis_b.data_ptr(),
                  self.vis_f.data_ptr())
-        for b, off, mt in zip(br, offs, mts):
-            self._op("bpb_head_branch_pool", b.t.data_ptr(), mt.data_ptr(), self.mask_sum.data_ptr(), n, b.h * b.w, b.c,
-                     off, ctot, kp1, h * w, self.pooled.data_ptr())
+        self.fork(range(1, len(br)))
+        for i, (b, off, mt) in enumerate(zip(br, offs, mts)):
+            with self.lane(i):
+                self._op("bpb_head_branch_pool", b.t.data_ptr(), mt.data_ptr(), self.mask_sum.data_ptr(), n, b.h * b.w,
+                         b.c, off, ctot, kp1, h * w, self.pooled.data_ptr())
+        self.join()
         return ctot
 
     def build_head_back(self, c):
@@ -556,11 +566,14 @@ class ForwardPlan:
         groups = [(m.global_after_pooling_dim_reduce, 0, n), (m.foreground_after_pooling_dim_reduce, n, n),
                   (m.background_after_pooling_dim_reduce, 2 * n, n), (m.parts_after_pooling_dim_reduce, 3 * n, K * n)]
         pooled2d = self.pooled.view(J * n, c)
-        for dr, r0, rows in groups:
+        self.fork(range(1, len(groups)))
+        for i, (dr, r0, rows) in enumerate(groups):
             fc, bn = dr.layers[0], dr.layers[1]
-            self._op("bpb_linear_tf32", pooled2d[r0:].data_ptr(), c, fc.weight.data_ptr(), fc.bias.data_ptr(),
-                     lin[r0:].data_ptr(), rows, D, c, D, 0, 0)
-            self._bn1d(lin[r0:], bn, self.emb[r0:], rows, D, relu=True)
+            with self.lane(i):
+                self._op("bpb_linear_tf32", pooled2d[r0:].data_ptr(), c, fc.weight.data_ptr(), fc.bias.data_ptr(),
+                         lin[r0:].data_ptr(), rows, D, c, D, 0, 0)
+                self._bn1d(lin[r0:], bn, self.emb[r0:], rows, D, relu=True)
+        self.join()
         # BN classifiers
         self.bn_emb = self._small((J * n, D))
         self.bn_conct = self._small((K * n, D))
@@ -572,20 +585,24 @@ class ForwardPlan:
             heads_parts = [(m.parts_identity_classifier, 3 * n, K * n)]
         else:
             heads_parts = [(m.parts_identity_classifier[k], (3 + k) * n, n) for k in range(K)]
-        for cl, r0 in heads:
-            self._bn_classifier(cl, self.emb[r0:], self.bn_emb[r0:], self.scores[r0:], n, D, ncls, ld)
-        for cl, r0, rows in heads_parts:
-            self._bn_classifier(cl, self.emb[r0:], self.bn_emb[r0:], self.scores[r0:], rows, D, ncls, ld)
+        # the identity heads are independent of each other: spread them over four stream lanes
+        self.fork(range(1, 4))
+        jobs = [(cl, r0, n) for cl, r0 in heads] + list(heads_parts)
+        for i, (cl, r0, rows) in enumerate(jobs):
+            with self.lane(i % 3):
+                self._bn_classifier(cl, self.emb[r0:], self.bn_emb[r0:], self.scores[r0:], rows, D, ncls, ld)
         # concat-parts classifier: BN1d over [N, K*D] == per-part BN1d with the matching parameter slice
         cc = m.concat_parts_identity_classifier
-        for k in range(K):
-            sl = slice(k * D, (k + 1) * D)
-            self._op("bpb_bn1d", self.emb[(3 + k) * n:].data_ptr(), cc.bn.weight[sl].data_ptr(),
-                     cc.bn.bias[sl].data_ptr(), BN_EPS, 0.1, cc.bn.running_mean[sl].data_ptr(),
-                     cc.bn.running_var[sl].data_ptr(), self.bn_conct[k * n:].data_ptr(), n, D, 0,
-                     1 if self.training else 0)
-        self._op("bpb_linear_tf32", self.bn_conct.data_ptr(), D, cc.classifier.weight.data_ptr(), None,
-                 self.scores_conct.data_ptr(), n, ncls, K * D, ld, 1, K)
+        with self.lane(3):
+            for k in range(K):
+                sl = slice(k * D, (k + 1) * D)
+                self._op("bpb_bn1d", self.emb[(3 + k) * n:].data_ptr(), cc.bn.weight[sl].data_ptr(),
+                         cc.bn.bias[sl].data_ptr(), BN_EPS, 0.1, cc.bn.running_mean[sl].data_ptr(),
+                         cc.bn.running_var[sl].data_ptr(), self.bn_conct[k * n:].data_ptr(), n, D, 0,
+                         1 if self.training else 0)
+            self._op("bpb_linear_tf32", self.bn_conct.data_ptr(), D, cc.classifier.weight.data_ptr(), None,
+                     self.scores_conct.data_ptr(), n, ncls, K * D, ld, 1, K)
+        self.join()
         self.ncls, self.ld, self.D = ncls, ld, D
 
     def _bn1d(self, x, bn, y, rows, c, relu):
