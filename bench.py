@@ -177,35 +177,56 @@ KERNELS_PER_CALL = {"bpb_pixel_classify": 3, "bpb_triplet_fwd": 3, "bpb_ce_ls_fw
 
 
 def roofline_probe(dev, peaks):
-    """Dominant kernel class = the tcgen05 3x3 conv at the stride-4 resolution (C=32, 64x32 map, batch 256):
-    23 % of the network's FLOPs and the largest single share of step time (profiles/).  Timed alone with CUDA events."""
+    """Dominant kernel class = the tcgen05 3x3 conv at the stride-4 resolution (C=32, 64x32 map, batch 256): 150 of the
+    662 launches and the largest single share of step time (profiles/launches_r1_step.md).  Its arithmetic intensity
+    (9.66 GFLOP / 67 MB = 144 FLOP/B) is below the machine balance (~250 FLOP/B), so the bound is HBM.
+    Timed with CUDA events around 8 back-to-back launches that rotate over 4 input/output pairs (4 x 67 MB > L2, so every
+    launch reads cold data and the host-side launch gap is amortised)."""
     from bpbreid_b200 import _lib
     n, h, w, c = PER_GPU_BATCH, 64, 32, 32
-    x = torch.randn(n, h, w, c, device=dev).to(torch.bfloat16)
+    sets = []
+    for _ in range(4):
+        x = torch.randn(n, h, w, c, device=dev).to(torch.bfloat16)
+        y = torch.empty(n, h, w, c, device=dev, dtype=torch.bfloat16)
+        sets.append((x, y))
     wt = (torch.randn(c, 9 * c, device=dev) * 0.05).to(torch.bfloat16)
-    y = torch.empty(n, h, w, c, device=dev, dtype=torch.bfloat16)
     tiles = _lib.query("bpb_conv_num_mtiles", n, h, w)
     stats = torch.empty(tiles, 2, c, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     s = torch.cuda.current_stream().cuda_stream
-    call = lambda: _lib.call("bpb_conv_bf16", x.data_ptr(), wt.data_ptr(), y.data_ptr(), stats.data_ptr(), n, h, w, c, c, 3, 1, 0, s)  # noqa: E731
-    for _ in range(3):
-        call()
+
+    def call(i):
+        x, y = sets[i % 4]
+        _lib.call("bpb_conv_bf16", x.data_ptr(), wt.data_ptr(), y.data_ptr(), stats.data_ptr(), n, h, w, c, c, 3, 1, 0, s)
+
+    for i in range(4):
+        call(i)
+    torch.cuda.synchronize()
+    reps, per = 10, 8
     times = []
-    for _ in range(10):
-        flush.zero_()
+    for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); call(); e1.record()
+        e0.record()
+        for i in range(per):
+            call(i)
+        e1.record()
         torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = float(np.mean(times))
+        times.append(e0.elapsed_time(e1) / per)
+    ms = float(np.median(times))
     flops = 2.0 * n * h * w * c * 9 * c
-    achieved = flops / (ms * 1e-3) / 1e12
     algo_bytes = n * h * w * c * 2 * 2 + 9 * c * c * 2 + tiles * 2 * c * 4
-    return {"bound": "tensor", "kernel": "tc_gemm_kernel<32,bf16,raw+stats> conv3x3 32->32 @64x32 bs256",
-            "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-            "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": algo_bytes,
-            "hbm_gbs_at_this_rate": algo_bytes / (ms * 1e-3) / 1e9, "peak_source": peaks["source"]}
+    achieved = algo_bytes / (ms * 1e-3) / 1e9
+    traffic = None
+    tf = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "roofline_traffic_r1.json")
+    if os.path.exists(tf):                                  # dram bytes per launch from one `ncu --set full` capture
+        try:
+            traffic = json.load(open(tf)).get("conv3x3_c32_bytes_per_launch")
+        except (OSError, ValueError):
+            traffic = None
+    return {"bound": "hbm", "kernel": "tc_gemm_kernel<32,bf16,raw+stats> conv3x3 32->32 @64x32 bs256",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": traffic, "ms_per_launch": ms, "algorithmic_bytes": algo_bytes,
+            "tflops_at_this_rate": flops / (ms * 1e-3) / 1e12, "tensor_peak_tflops": peaks["bf16_tflops"],
+            "peak_source": peaks["source"]}
 
 
 def run_gpu_arm(args, rank, world):

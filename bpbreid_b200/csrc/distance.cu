@@ -53,6 +53,13 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ x
 
 __global__ void init_max_kernel(float* scratch) { scratch[0] = -1.f; }
 
+// 32-byte store (STG.256): a lane writes one full sector, so a row segment costs half the LSU requests of float4 stores
+__device__ __forceinline__ void st_global_v8(float* p, const float (&o)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
+                 "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                 : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // SIMT path (any D; also the on-device cross-check of the tensor-core path)
 // ----------------------------------------------------------------------------------------------
@@ -306,7 +313,9 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
         const int et = ew * 32 + lane;           // 0..511
         float local_max = -1.f;
         uint32_t acc_it = 0;
-        const bool vec_ok = (a.ng & 3) == 0;
+        // 32-byte vector stores need 32-byte aligned row segments
+        const bool vec_ok = (a.ng & 7) == 0 && (reinterpret_cast<uintptr_t>(a.dist) & 31) == 0 &&
+                            (a.part_dist == nullptr || (reinterpret_cast<uintptr_t>(a.part_dist) & 31) == 0);
         for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
             int tq, tg;
             dist_tile_coords(t, a.tiles_q, a.tiles_g, tq, tg);
@@ -360,12 +369,12 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
                         if (lane == 0) mbar_arrive_a(acce_a + buf * 8);
                     }
 #pragma unroll
-                    for (int u4 = 0; u4 < 16; u4 += 4) {
-                        float o[4];
+                    for (int u8 = 0; u8 < 16; u8 += 8) {
+                        float o[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int u = cch * 16 + u4 + e;
-                            const float dot = __uint_as_float(v[u4 + e]);
+                        for (int e = 0; e < 8; ++e) {
+                            const int u = cch * 16 + u8 + e;
+                            const float dot = __uint_as_float(v[u8 + e]);
                             float dv;
                             if (kEuclid) dv = sqrtf(fmaxf(qsv - 2.f * dot + gs_p[u], 0.f));
                             else dv = 1.f - dot;
@@ -379,13 +388,13 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
                             else num[u] += dv * w;
                         }
                         if (prow) {
-                            const int jb = jc + cch * 16 + u4;
-                            if (vec_ok && jb + 4 <= a.ng) {
-                                *reinterpret_cast<float4*>(prow + cch * 16 + u4) = make_float4(o[0], o[1], o[2], o[3]);
+                            const int jb = jc + cch * 16 + u8;
+                            if (vec_ok && jb + 8 <= a.ng) {
+                                st_global_v8(prow + cch * 16 + u8, o);
                             } else {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (jb + e < a.ng) prow[cch * 16 + u4 + e] = o[e];
+                                for (int e = 0; e < 8; ++e)
+                                    if (jb + e < a.ng) prow[cch * 16 + u8 + e] = o[e];
                             }
                         }
                     }
@@ -395,11 +404,11 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
             if (row_ok) {
                 float* drow = a.dist + static_cast<int64_t>(i) * a.ng + jc;
 #pragma unroll
-                for (int u4 = 0; u4 < 64; u4 += 4) {
-                    float o[4];
+                for (int u8 = 0; u8 < 64; u8 += 8) {
+                    float o[8];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int u = u4 + e;
+                    for (int e = 0; e < 8; ++e) {
+                        const int u = u8 + e;
                         float r = num[u];
                         if (!kMax) {
                             if (kVis == VIS_NONE) {
@@ -417,13 +426,13 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
                         }
                         o[e] = r;
                     }
-                    const int jb = jc + u4;
-                    if (vec_ok && jb + 4 <= a.ng) {
-                        *reinterpret_cast<float4*>(drow + u4) = make_float4(o[0], o[1], o[2], o[3]);
+                    const int jb = jc + u8;
+                    if (vec_ok && jb + 8 <= a.ng) {
+                        st_global_v8(drow + u8, o);
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (jb + e < a.ng) drow[u4 + e] = o[e];
+                        for (int e = 0; e < 8; ++e)
+                            if (jb + e < a.ng) drow[u8 + e] = o[e];
                     }
                 }
             }
