@@ -53,9 +53,10 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ x
 
 __global__ void init_max_kernel(float* scratch) { scratch[0] = -1.f; }
 
-// 32-byte store (STG.256): a lane writes one full sector, so a row segment costs half the LSU requests of float4 stores
+// 32-byte streaming store (STG.EF.256): a lane writes one full sector (half the LSU requests of float4 stores) and the
+// evict-first hint keeps the 1.9 GB output stream from pushing the L2-resident gallery tiles out
 __device__ __forceinline__ void st_global_v8(float* p, const float (&o)[8]) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
                  "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
                  : "memory");
 }

@@ -16,6 +16,7 @@ static inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + 
 
 constexpr int kMaxMatches = 2048;
 constexpr int kMatchBatch = 16;
+constexpr int kMaxJunk = 512;     // same pid AND same camera entries per query (removed from the ranking, rank.py:124-127)
 
 __global__ void __launch_bounds__(256) rank_query_kernel(const float* __restrict__ dist,
                                                          const int64_t* __restrict__ q_pids,
@@ -27,22 +28,33 @@ __global__ void __launch_bounds__(256) rank_query_kernel(const float* __restrict
     __shared__ int m_idx[kMaxMatches];
     __shared__ float m_d[kMaxMatches];
     __shared__ int m_rank[kMaxMatches];
-    __shared__ int m_count;
+    __shared__ int m_count, j_count;
     __shared__ int cnt[kMatchBatch];
+    __shared__ int junk_idx[kMaxJunk];
+    __shared__ float junk_d[kMaxJunk];
     const int q = blockIdx.x;
     const int64_t qp = q_pids[q], qc = q_camids[q];
     const float* row = dist + static_cast<int64_t>(q) * ng;
-    if (threadIdx.x == 0) m_count = 0;
+    if (threadIdx.x == 0) { m_count = 0; j_count = 0; }
     __syncthreads();
     // 1. matches = same pid, different camera (kept & relevant)
+    //    junk = same pid, same camera (dropped).  The gallery ids are read ONCE: the counting pass below runs over the
+    //    whole row and the few junk entries are subtracted afterwards.
     for (int j = threadIdx.x; j < ng; j += blockDim.x) {
-        if (g_pids[j] == qp && g_camids[j] != qc) {
-            const int slot = atomicAdd(&m_count, 1);
-            if (slot < kMaxMatches) { m_idx[slot] = j; m_d[slot] = row[j]; }
+        if (g_pids[j] == qp) {
+            if (g_camids[j] != qc) {
+                const int slot = atomicAdd(&m_count, 1);
+                if (slot < kMaxMatches) { m_idx[slot] = j; m_d[slot] = row[j]; }
+            } else {
+                const int slot = atomicAdd(&j_count, 1);
+                if (slot < kMaxJunk) { junk_idx[slot] = j; junk_d[slot] = row[j]; }
+            }
         }
     }
     __syncthreads();
     const int nm = m_count;
+    const int nj = j_count;
+    const bool junk_listed = nj <= kMaxJunk;              // else: fall back to re-reading the ids in the counting pass
     if (nm == 0 || nm > kMaxMatches) {
         if (threadIdx.x == 0) {
             first_rank[q] = -1; ap64[q] = 0.0; ap32[q] = 0.f;
@@ -63,12 +75,28 @@ __global__ void __launch_bounds__(256) rank_query_kernel(const float* __restrict
             mi[t] = t < nb ? m_idx[b0 + t] : -1;
             local[t] = 0;
         }
-        for (int j = threadIdx.x; j < ng; j += blockDim.x) {
-            const bool kept = !(g_pids[j] == qp && g_camids[j] == qc);
-            if (!kept) continue;
-            const float dj = row[j];
+        if (junk_listed) {
+#pragma unroll 4
+            for (int j = threadIdx.x; j < ng; j += blockDim.x) {
+                const float dj = row[j];
 #pragma unroll
-            for (int t = 0; t < kMatchBatch; ++t) local[t] += (dj < md[t] || (dj == md[t] && j < mi[t])) ? 1 : 0;
+                for (int t = 0; t < kMatchBatch; ++t) local[t] += (dj < md[t] || (dj == md[t] && j < mi[t])) ? 1 : 0;
+            }
+            // take the junk entries back out (each was counted once above)
+            for (int u = threadIdx.x; u < nj; u += blockDim.x) {
+                const float dj = junk_d[u];
+                const int j = junk_idx[u];
+#pragma unroll
+                for (int t = 0; t < kMatchBatch; ++t) local[t] -= (dj < md[t] || (dj == md[t] && j < mi[t])) ? 1 : 0;
+            }
+        } else {
+            for (int j = threadIdx.x; j < ng; j += blockDim.x) {
+                const bool kept = !(g_pids[j] == qp && g_camids[j] == qc);
+                if (!kept) continue;
+                const float dj = row[j];
+#pragma unroll
+                for (int t = 0; t < kMatchBatch; ++t) local[t] += (dj < md[t] || (dj == md[t] && j < mi[t])) ? 1 : 0;
+            }
         }
 #pragma unroll
         for (int t = 0; t < kMatchBatch; ++t) {

@@ -69,7 +69,7 @@ enum Epi { EPI_RAW_STATS = 0, EPI_F32_BIAS = 1 };
 // address).  A-operand traffic from L2 drops from 9 to 3*(rows+2)/rows tiles per output tile and every ring stage
 // carries three taps' worth of MMAs, which amortises the single-thread issue loop.
 template <int BN, bool kTf32, int kEpi>
-__global__ void __launch_bounds__(kMaxThreads) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
