@@ -273,25 +273,29 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
             } else {
                 // previous tile's readers of the staging buffer must be done before it is overwritten
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    tmem_ld_wait();
-                    for (int ww = 1; ww < W; ++ww) {
-                        uint32_t u[32];
-                        tmem_ld32(taddr + ww * BN + c0, u);
-                        tmem_ld_wait();
+                // 16-column chunks: the W partial accumulators of a chunk are requested together and waited for once
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t v[16], u1[16], u2[16];
+                    tmem_ld16(taddr + c0, v);
+                    if (W > 1) tmem_ld16(taddr + BN + c0, u1);
+                    if (W > 2) tmem_ld16(taddr + 2 * BN + c0, u2);
+                    tmem_ld_wait();
+                    if (W > 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u1[j]));
                     }
-                    if (c0 + 32 >= BN) {
+                    if (W > 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u2[j]));
+                    }
+                    if (c0 + 16 >= BN) {
                         tc_fence_before();
                         mbar_arrive_a(acce_a + buf * 8);
                     }
                     uint4* dst = reinterpret_cast<uint4*>(epi_tile + row * kPitch + c0 * 2);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 2; ++j) {
                         uint4 o;
                         o.x = pack_bf16(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
                         o.y = pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
@@ -301,16 +305,34 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
                     }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                // ---- coalesced 16-byte stores of the tile (issued first: their latency hides under the statistics) ----
+                {
+                    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+                    constexpr int kChunksPerRow = BN / 8;
+#pragma unroll 4
+                    for (int ch = et; ch < kTileM * kChunksPerRow; ch += 128) {
+                        const int r = ch / kChunksPerRow, cc = ch % kChunksPerRow;
+                        if (r < valid_rows) {
+                            const uint4 o = *reinterpret_cast<const uint4*>(epi_tile + r * kPitch + cc * 16);
+                            *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + r) * p.ldo + c_base + cc * 8) = o;
+                        }
+                    }
+                }
                 // ---- per-tile column statistics from the bf16-rounded values ----
                 if (p.stats != nullptr || fused_bn) {
                     constexpr int kPairs = BN / 2;
                     constexpr int kGroups = 128 / kPairs;                   // BN=32:8, 64:4, 128:2
+                    constexpr int kRowsPer = kTileM / kGroups;              // rows each thread adds up
                     const int pair = et % kPairs, grp = et / kPairs;
                     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                    for (int r = grp; r < valid_rows; r += kGroups) {
-                        const uint32_t u = *reinterpret_cast<const uint32_t*>(epi_tile + r * kPitch + pair * 4);
-                        const float a = bf16_lo(u), b = bf16_hi(u);
-                        s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+                    const uint8_t* src = epi_tile + grp * kPitch + pair * 4;
+#pragma unroll 8
+                    for (int i = 0; i < kRowsPer; ++i) {
+                        if (grp + i * kGroups < valid_rows) {
+                            const uint32_t u = *reinterpret_cast<const uint32_t*>(src + i * kGroups * kPitch);
+                            const float a = bf16_lo(u), b = bf16_hi(u);
+                            s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+                        }
                     }
                     red_smem[0][grp][pair * 2 + 0] = s0; red_smem[0][grp][pair * 2 + 1] = s1;
                     red_smem[1][grp][pair * 2 + 0] = q0; red_smem[1][grp][pair * 2 + 1] = q1;
@@ -328,16 +350,6 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
                             cta_stats[c_base + et] += s;
                             cta_stats[p.N + c_base + et] += qq;
                         }
-                    }
-                }
-                // ---- coalesced 16-byte stores of the tile ----
-                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-                constexpr int kChunksPerRow = BN / 8;
-                for (int ch = et; ch < kTileM * kChunksPerRow; ch += 128) {
-                    const int r = ch / kChunksPerRow, cc = ch % kChunksPerRow;
-                    if (r < valid_rows) {
-                        const uint4 o = *reinterpret_cast<const uint4*>(epi_tile + r * kPitch + cc * 16);
-                        *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + r) * p.ldo + c_base + cc * 8) = o;
                     }
                 }
             }
