@@ -163,22 +163,15 @@ __global__ void __launch_bounds__(256) lowres_logits_kernel(const uint4* __restr
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cvec = cb / 8;
-    // a branch with fewer than 32 channel vectors (C = 128) lets the warp split into lane groups that take other rows
-    int lpp = cvec >= 32 ? 32 : cvec;                    // lanes per row group
-    if (lpp < 4 || (32 % lpp) != 0) lpp = 32;           // (a lane group must hold the 4 writer lanes)
-    const int groups = 32 / lpp;
-    const int sub = lane / lpp, cl = lane - sub * lpp;
-    const int rows_per_iter = 4 * groups;
     const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-    for (int64_t wbase = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * rows_per_iter; wbase < rows;
-         wbase += warps_total * rows_per_iter) {
-        const int64_t base = wbase + sub * 4;
+    for (int64_t base = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + warp) * 4; base < rows;
+         base += warps_total * 4) {
         float acc[4][KP1];
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
             for (int k = 0; k < KP1; ++k) acc[p][k] = 0.f;
-        for (int cv = cl; cv < cvec; cv += lpp) {
+        for (int cv = lane; cv < cvec; cv += 32) {
             float f[4][8];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
@@ -198,14 +191,10 @@ __global__ void __launch_bounds__(256) lowres_logits_kernel(const uint4* __restr
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int k = 0; k < KP1; ++k) {
-                float v = acc[p][k];
-                for (int o = lpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // inside the lane group
-                acc[p][k] = v;
-            }
+            for (int k = 0; k < KP1; ++k) acc[p][k] = warp_sum(acc[p][k]);
 #pragma unroll
         for (int p = 0; p < 4; ++p)
-            if (cl == p && base + p < rows) {
+            if (lane == p && base + p < rows) {
 #pragma unroll
                 for (int k = 0; k < KP1; ++k) out[(base + p) * KP1 + k] = acc[p][k];
             }
