@@ -272,6 +272,42 @@ def test_training_forward_and_loss_are_finite_and_consistent():
     assert abs(float(loss) - float(o_loss)) < 1e-3 * abs(float(o_loss))
 
 
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cuda_graph"])
+def test_stream_lane_schedule_is_race_free(monkeypatch, graph):
+    """The plan records HRNet branches / fuse outputs / head groups on four stream lanes (fork/join).  A missing
+    dependency or a buffer reused across lanes would corrupt activations, so the multi-stream schedule must reproduce
+    itself and the single-stream schedule.  Eval mode (well conditioned; the only run-to-run freedom left is the order of
+    the shared-memory float atomics in the pixel head, ~1e-7)."""
+    def run(single):
+        monkeypatch.setenv("BPB_SINGLE_STREAM", "1" if single else "0")
+        c = GI.model_case("hrnet32_k5")
+        m = c["model"]
+        m.load_state_dict(c["state_dict"])
+        m = m.to(DEV)
+        m.train(False)
+        m.use_cuda_graph = graph
+        x = torch.from_numpy(c["images"]).to(DEV)
+        outs = []
+        with torch.no_grad():
+            for _ in range(3):
+                emb, vis, ids, pix, _, masks = m(x)
+                torch.cuda.synchronize()
+                outs.append([t.float().clone() for t in (emb["parts"], emb["bn_globl"], ids["conct"], pix)])
+        pl = next(iter(m._plans.values()))
+        return outs, {op[3] for op in pl.ops}
+
+    multi, lanes_m = run(False)
+    single, lanes_s = run(True)
+    assert lanes_m == {0, 1, 2, 3} and lanes_s == {0}
+
+    def close(a, b):
+        return float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-7
+
+    for other in (multi[1], multi[2], single[0]):
+        for a, b in zip(multi[0], other):
+            assert close(a, b)
+
+
 def test_tc_and_simt_conv_paths_agree_in_eval_mode():
     _, _, out_tc = _run_model("hrnet32_k5", False, "tc")
     _, _, out_ref = _run_model("hrnet32_k5", False, "ref")
