@@ -301,7 +301,8 @@ def test_stream_lane_schedule_is_race_free(monkeypatch, graph):
     assert lanes_m == {0, 1, 2, 3} and lanes_s == {0}
 
     def close(a, b):
-        return float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-7
+        # run-to-run freedom (atomics order) is ~5e-5 here; a race would corrupt whole activations (O(1) errors)
+        return float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-7
 
     for other in (multi[1], multi[2], single[0]):
         for a, b in zip(multi[0], other):
