@@ -20,6 +20,8 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
                  int ksize, int stride, int bn_hint, const BnFuse* bn, cudaStream_t stream);
 int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bias, float* out, int m, int n, int k,
                    int ldo, int a_mode, int a_parts, cudaStream_t stream);
+int conv3x3_halo_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, const BnFuse* bn,
+                      cudaStream_t stream);
 int conv_num_mtiles(int n, int ho, int wo);
 
 // ---- nn_kernels.cu ----------------------------------------------------------------------------

@@ -511,6 +511,14 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (wd + 2 * pad - ksize) / stride + 1;
     BPB_CHECK(cin % 32 == 0 && cout % 32 == 0, "conv_bf16_tc: channels must be multiples of 32 (cin=%d cout=%d)", cin,
               cout);
+    // bn_hint bit 10: run narrow 3x3 stride-1 layers from one halo tile per output tile (tc_conv_halo.cu).  Opt-in:
+    // it cuts the L2 -> SM operand stream 2.5x but was measured SLOWER than the row-shift schedule (44 vs 39 us for
+    // the C=32 layer, 13.0 vs 12.5 ms per step) -- the bound is the per-tile latency chain, not L2 bandwidth.
+    if (ksize == 3 && stride == 1 && stats == nullptr && (bn_hint & 0x400) != 0) {
+        const int rc = conv3x3_halo_bf16(x, w, y, n, h, wd, cin, cout, bn, stream);
+        if (rc >= 0) return rc;
+    }
+    bn_hint &= ~0x400;
     BPB_CHECK(wo <= 128 && 128 % wo == 0, "conv_bf16_tc: output width %d must divide 128", wo);
     const int bh = (128 / wo) < ho ? (128 / wo) : ho;
     BPB_CHECK(ho % bh == 0, "conv_bf16_tc: output height %d not a multiple of tile rows %d", ho, bh);

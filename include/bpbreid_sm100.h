@@ -31,6 +31,9 @@ int bpb_abi_version(void);
  * Replaces: torchreid/models/hrnet.py:60-64,80-96,116-137,222-257,459-483; torchreid/models/resnet.py:43-63,128-154. */
 int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                   int ksize, int stride, int bn_hint, void* stream);
+/* bn_hint: 0 = automatic tile width; 32/64/128 forces the N tile; bit 8 (0x100) forces the one-tap-per-stage schedule
+ * for 3x3 stride-1 layers; bit 10 (0x400) opts in to the single-halo-tile schedule (csrc/tc_conv_halo.cu; Cout 32/64,
+ * no per-tile `stats`).  The bits only select between numerically equivalent schedules (test / tuning hooks). */
 int bpb_conv_num_mtiles(int n, int ho, int wo);
 /* Same convolution with the train-mode BatchNorm that follows it fused into the launch (conv + nn.BatchNorm2d call
  * pairs, e.g. hrnet.py:82-83): every CTA adds its per-channel sums to `bn_workspace` (fp64 atomics) and the last CTA

@@ -127,6 +127,55 @@ def test_conv_fused_bn_matches_two_pass_statistics():
     assert int(ws.count_nonzero()) == 0
 
 
+HALO_SHAPES = [(4, 64, 32, 32, 32), (4, 32, 16, 64, 64), (3, 64, 32, 64, 64), (2, 16, 8, 64, 32), (5, 7, 32, 32, 64),
+               (2, 96, 32, 32, 32), (3, 10, 12, 32, 32)]
+
+
+@pytest.mark.parametrize("shape", HALO_SHAPES, ids=[str(s) for s in HALO_SHAPES])
+def test_conv_halo_tile_kernel(shape):
+    """3x3 stride-1 layers with <= 64 output channels run from ONE zero-padded halo tile per output tile (all nine taps
+    are descriptor offsets into it, csrc/tc_conv_halo.cu); opt-in through bn_hint bit 10 (measured slower than the
+    row-shift kernel, kept as the evidence that L2 -> SM bandwidth is not the bound).
+    Checked against the fp32 reference, against the row-shift kernel, and (fused BatchNorm) against statistics taken
+    from the stored outputs.  Shapes include ragged last tiles (H not a multiple of the rows per tile) and odd widths."""
+    n, h, w, cin, cout = shape
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).to(DEV)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5).to(DEV)
+    wp = pack_w(wt)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2), None, 1, 1)
+    ref = ref.permute(0, 2, 3, 1)
+    ya = torch.full((n, h, w, cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    _lib.call("bpb_conv_bf16", x.data_ptr(), wp.data_ptr(), ya.data_ptr(), None, n, h, w, cin, cout, 3, 1, 0x400, S())
+    torch.cuda.synchronize()
+    assert torch.isfinite(ya.float()).all()
+    assert rel_err(ya.float(), ref) < 1e-2
+    bh = min(h, 128 // w) if 128 % w == 0 else 0
+    if bh and h % bh == 0 and (128 // (w * bh)) * w * bh == 128:        # shapes the row-shift kernel tiles
+        yb = torch.empty_like(ya)
+        _lib.call("bpb_conv_bf16", x.data_ptr(), wp.data_ptr(), yb.data_ptr(), None, n, h, w, cin, cout, 3, 1, 0, S())
+        torch.cuda.synchronize()
+        assert rel_err(ya.float(), yb.float()) < 4e-3        # one bf16 ulp where the fp32 sums round differently
+    # fused train-mode BatchNorm: scale / shift from the statistics of the stored (bf16) outputs
+    ws = torch.zeros(_lib.query("bpb_conv_bn_workspace_bytes", cout), dtype=torch.uint8, device=DEV)
+    gam, bet = torch.rand(cout, device=DEV) + 0.5, torch.randn(cout, device=DEV)
+    rm, rv = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+    sc, sh = torch.empty(cout, device=DEV), torch.empty(cout, device=DEV)
+    yc = torch.empty_like(ya)
+    for _ in range(2):                                       # twice: the workspace must come back zeroed
+        _lib.call("bpb_conv_bn_bf16", x.data_ptr(), wp.data_ptr(), yc.data_ptr(), None, n, h, w, cin, cout, 3, 1, 0x400,
+                  ws.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(), 0,
+                  sc.data_ptr(), sh.data_ptr(), S())
+    torch.cuda.synchronize()
+    assert torch.equal(yc, ya)
+    flat = yc.float().reshape(-1, cout).double()
+    mean, var = flat.mean(0), flat.var(0, unbiased=False)
+    sc_ref = (gam.double() / torch.sqrt(var + 1e-5)).float()
+    sh_ref = (bet.double() - mean * gam.double() / torch.sqrt(var + 1e-5)).float()
+    assert rel_err(sc, sc_ref) < 1e-4 and rel_err(sh, sh_ref) < 1e-4
+    assert int(ws.view(torch.int32).abs().sum()) == 0
+
+
 def test_conv_bn_hint_variants():
     n, h, w, cin, cout, k, s = 4, 32, 16, 64, 128, 3, 1
     g = torch.Generator().manual_seed(3)
