@@ -12,6 +12,8 @@
 // warps 2..5 = epilogue (TMEM -> registers -> smem tile -> coalesced global stores + BN partial sums).
 // Reference semantics replaced: nn.Conv2d / nn.Linear call sites of torchreid/models/hrnet.py:67-137,
 // 211-257,449-483, torchreid/models/resnet.py:105-154, torchreid/models/bpbreid.py:324-350,398-415.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -460,7 +462,7 @@ static int pow2_cols(int c) {
 
 // Pick the number of MMA-issuing warps W (must divide k_iters), the TMEM allocation and the ring depth so that
 // (issuers per SM) = W x (CTAs per SM) is maximal: TMEM allows 512 / pow2(2*W*BN) CTAs, shared memory the rest.
-static void choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_bytes) {
+static void choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_bytes, int max_w = kMaxMmaWarps) {
     // The ring depth must be a multiple of W: then every ring slot is always consumed by the same MMA warp, which is
     // what the mbarrier parity protocol needs (a warp that shares a slot with another warp could skip a phase and
     // mistake an old completion for the one it is waiting for).
@@ -470,7 +472,9 @@ static void choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_by
     // first pass: every MMA warp gets two ring slots (prefetch distance); second pass: one slot each
     // (a first pass that demanded two slots per warp was measured slower: it trades CTAs per SM for ring depth)
     for (int slots_per_warp = 1; slots_per_warp >= 1 && best_issuers == 0; --slots_per_warp) {
-        for (int w = kMaxMmaWarps; w >= 1; --w) {
+        static const int w_env = [] { const char* e = getenv("BPB_CONV_MAX_W"); return e ? atoi(e) : 0; }();   // tuning hook
+        const int w_cap = w_env > 0 ? w_env : max_w;
+        for (int w = (w_cap < kMaxMmaWarps ? w_cap : kMaxMmaWarps); w >= 1; --w) {
             if (p.k_iters % w) continue;
             const int cols = pow2_cols(2 * w * bn_tile);
             if (cols > 512) continue;
@@ -567,7 +571,12 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     const int m_tiles = (p.M + kTileM - 1) / kTileM;
     int bn_tile = pick_bn(m_tiles, cout, bn_hint);
     if (bn_hint == 0 && ksize == 3 && bn_tile > 64) bn_tile = 64;       // narrow tiles + several issuers beat one N=128 issuer
-    choose_issue_config(p, bn_tile, (rowshift ? 3 : 1), kTileM * (bn_tile * 2 + 16) + (bn ? 8 * cout : 0));
+    // Layers with many tiles (>= 4096: the stride-4 maps at batch 256) run faster as three CTAs per SM with ONE MMA
+    // warp each (three epilogues, three producers in flight) than as two CTAs with three MMA warps (measured: C=32 3x3
+    // 34.8 vs 38.9 us, stem conv2 84 vs 92 us); the small low-resolution layers prefer the wide CTAs.
+    const int total_tiles_h = m_tiles * ((cout + bn_tile - 1) / bn_tile);
+    choose_issue_config(p, bn_tile, (rowshift ? 3 : 1), kTileM * (bn_tile * 2 + 16) + (bn ? 8 * cout : 0),
+                        total_tiles_h >= 4096 ? 1 : kMaxMmaWarps);
 
     const CUtensorMapSwizzle sw = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tmA, tmB;
