@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
                 }
                 const float* gs_p = s_gs + pp * kDN + cg * 64;
                 const float* gw_p = s_gw + pp * kDN + cg * 64;
-                float* prow = (a.part_dist && row_ok)
+                // (a part the query does not show is rewritten as a whole row by the fix-up: skip its stores here)
+                float* prow = (a.part_dist && row_ok && !(kVis == VIS_BOOL && qw == 0.f))
                                   ? a.part_dist + (static_cast<int64_t>(pp) * a.nq + i) * a.ng + jc : nullptr;
                 mbar_wait_a(accf_a + buf * 8, use & 1);
                 tc_fence_after();
