@@ -156,7 +156,9 @@ int bpb_weighted_sum(const float* const* terms, const float* weights, int n, flo
  *      torchreid/metrics/rank_cylib/rank_cy.pyx:154-249 ----------------------------------------------------- */
 
 /* qf [nq, p, d], gf [ng, p, d] fp32.  metric 0 euclidean / 1 cosine; strat 0 mean / 1 max; impl 0 tcgen05 (tf32),
- * 1 SIMT fp32.  dist [nq, ng]; part_dist [p, nq, ng] or NULL; scratch >= bpb_part_distance_scratch_floats(). */
+ * 1 SIMT fp32.  dist [nq, ng]; part_dist [p, nq, ng] or NULL; scratch >= bpb_part_distance_scratch_floats().
+ * impl 0 numerics: tf32 products with fp32 accumulation, norms taken from the tf32-truncated inputs, sqrt.approx
+ * (absolute error <= ~2e-3 on unit-norm features, tests/test_gpu_path.py); impl 1 is plain fp32 with IEEE sqrt. */
 int bpb_part_distance(const float* qf, const float* gf, const void* qv, const void* gv, int vis_mode, int nq, int ng,
                       int p, int d, int metric, int strat, int impl, float* dist, float* part_dist, float* scratch,
                       void* stream);
