@@ -20,14 +20,14 @@ _F = ctypes.c_float
 _SIGS = {
     "bpb_conv_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpb_conv_num_mtiles": [_I, _I, _I],
-    "bpb_conv_bn_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I, _P, _P, _P],
+    "bpb_conv_bn_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I, _P, _P, _P, _P],
     "bpb_conv_bn_workspace_bytes": [_I],
     "bpb_conv_ref_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpb_stem_conv": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bpb_stem_conv_tiles": [_I, _I, _I],
     "bpb_colstats_bf16": [_P, _P, _I, _I, _P],
     "bpb_colstats_tiles": [_I],
-    "bpb_bn_finalize": [_P, _I, _I, _I, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P],
+    "bpb_bn_finalize": [_P, _I, _I, _I, _L, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P],
     "bpb_bn_eval_fold": [_P, _P, _P, _P, _F, _I, _P, _P, _P],
     "bpb_bn_apply": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
     "bpb_fuse_sum": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
@@ -53,6 +53,26 @@ _SIGS = {
     "bpb_part_distance_scratch_floats": [_I, _I, _I],
     "bpb_rank_market1501": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "bpb_argsort_rows": [_P, _I, _I, _P, _P],
+    "bpb_l2_normalize": [_P, _P, _L, _I, _F, _P],
+    "bpb_conv_wgrad_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "bpb_relu_grad_sum": [_P, _I, _P, _P, _L, _I, _P],
+    "bpb_bn_bwd_workspace_bytes": [_I],
+    "bpb_bn_bwd_reduce": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "bpb_bn_bwd_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "bpb_stem_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "bpb_adam_pack": [_P, _I, _L, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _I, _P],
+    "bpb_param_segment_bytes": [],
+    "bpb_transpose_pad": [_P, _L, _I, _I, _P, _L, _I, _I, _P],
+    "bpb_ce_ls_bwd": [_P, _L, _P, _P, _I, _I, _F, _F, _P, _L, _P],
+    "bpb_triplet_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _P],
+    "bpb_bn1d_bwd": [_P, _L, _P, _L, _P, _L, _P, _F, _I, _I, _P, _L, _I, _P, _P, _P],
+    "bpb_colsum_f32": [_P, _L, _I, _I, _P, _P],
+    "bpb_head_pool_bwd_prep": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "bpb_head_dmask": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "bpb_head_pixel_bwd": [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _F, _F, _P, _P, _P],
+    "bpb_head_dwf": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "bpb_pixel_fold_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P, _P, _P, _P, _P, _P],
+    "bpb_head_branch_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
 }
 _PLAIN_INT = {"bpb_conv_num_mtiles", "bpb_colstats_tiles", "bpb_abi_version", "bpb_stem_conv_tiles"}
 
@@ -79,7 +99,8 @@ def load():
     for name, sig in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = sig
-        fn.restype = _L if name in ("bpb_part_distance_scratch_floats", "bpb_conv_bn_workspace_bytes") else _I
+        fn.restype = _L if name in ("bpb_part_distance_scratch_floats", "bpb_conv_bn_workspace_bytes",
+                                    "bpb_bn_bwd_workspace_bytes") else _I
     _lib = lib
     return lib
 

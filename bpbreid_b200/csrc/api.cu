@@ -24,6 +24,19 @@ int check_cuda(cudaError_t e, const char* what) {
     return 1;
 }
 
+int device_sm_count() {
+    static int cache[128] = {0};
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 0;
+    if (dev < 0 || dev >= 128) dev = 0;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (check_cuda(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return 0;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -75,7 +88,7 @@ using namespace bpb;
 extern "C" {
 
 const char* bpb_last_error(void) { return g_err; }
-int bpb_abi_version(void) { return 1; }
+int bpb_abi_version(void) { return 2; }
 
 int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                   int ksize, int stride, int bn_hint, void* stream) {
@@ -84,8 +97,8 @@ int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, in
 int bpb_conv_bn_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                      int ksize, int stride, int bn_hint, void* bn_workspace, const float* gamma, const float* beta,
                      float eps, float momentum, float* running_mean, float* running_var, int c_lo, float* scale,
-                     float* shift, void* stream) {
-    BnFuse bn{bn_workspace, gamma, beta, running_mean, running_var, scale, shift, eps, momentum, c_lo};
+                     float* shift, float* save_mean_invstd, void* stream) {
+    BnFuse bn{bn_workspace, gamma, beta, running_mean, running_var, scale, shift, eps, momentum, c_lo, save_mean_invstd};
     return conv_bf16_tc(x, w, y, stats, n, h, wd, cin, cout, ksize, stride, bn_hint, &bn, S(stream));
 }
 int64_t bpb_conv_bn_workspace_bytes(int cout) { return static_cast<int64_t>(cout) * 2 * 8 + 16; }
@@ -105,9 +118,9 @@ int bpb_colstats_bf16(const void* x, float* partials, int m, int c, void* stream
 int bpb_colstats_tiles(int m) { return colstats_tiles(m); }
 int bpb_bn_finalize(const float* partials, int tiles, int c, int c_lo, int64_t count, const float* gamma,
                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                    float* scale, float* shift, void* stream) {
+                    float* scale, float* shift, float* save_mean_invstd, void* stream) {
     return bn_finalize(partials, tiles, c, c_lo, count, gamma, beta, eps, momentum, running_mean, running_var, scale,
-                       shift, S(stream));
+                       shift, save_mean_invstd, S(stream));
 }
 int bpb_bn_eval_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                      float eps, int c, float* scale, float* shift, void* stream) {
@@ -219,6 +232,95 @@ int bpb_rank_market1501(const float* dist, const int64_t* q_pids, const int64_t*
 }
 int bpb_argsort_rows(const float* dist, int nq, int ng, int32_t* indices, void* stream) {
     return argsort_rows(dist, nq, ng, indices, S(stream));
+}
+
+/* ---- training backward ---- */
+int bpb_conv_wgrad_bf16(const void* x, const void* dy, float* dw, int n, int h, int wd, int cin, int cout, int ksize,
+                        int stride, int dy_up, void* stream) {
+    return conv_wgrad_tc(x, dy, dw, n, h, wd, cin, cout, ksize, stride, dy_up, S(stream));
+}
+int bpb_relu_grad_sum(const void* const* srcs, int nsrc, const void* y, void* out, int64_t m, int c, void* stream) {
+    return relu_grad_sum(srcs, nsrc, y, out, m, c, S(stream));
+}
+int64_t bpb_bn_bwd_workspace_bytes(int c) { return static_cast<int64_t>(c) * 2 * 8 + 16; }
+int bpb_bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
+                      int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,
+                      float* dgamma, float* dbeta, void* stream) {
+    return bn_bwd_reduce(dy, raw, mean_invstd, scale, shift, n, h, w, c, up_log2, relu_affine, c_lo, workspace, coef,
+                         dgamma, dbeta, S(stream));
+}
+int bpb_bn_bwd_apply(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
+                     const float* coef, int n, int h, int w, int c, int up_log2, int relu_affine, int zero_insert,
+                     void* draw, void* stream) {
+    return bn_bwd_apply(dy, raw, mean_invstd, scale, shift, coef, n, h, w, c, up_log2, relu_affine, zero_insert, draw,
+                        S(stream));
+}
+int bpb_stem_wgrad(const float* img, const void* draw, float* dw, int n, int h, int wd, int cout, int ksize, int stride,
+                   void* stream) {
+    return stem_wgrad(img, draw, dw, n, h, wd, cout, ksize, stride, S(stream));
+}
+int bpb_adam_pack(const void* segs, int nseg, int64_t total, float* p, const float* g, float* m, float* v, float lr,
+                  float beta1, float beta2, float eps, float wd, int step, float grad_scale, int do_update,
+                  void* stream) {
+    return adam_pack(segs, nseg, total, p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale, do_update, S(stream));
+}
+int bpb_param_segment_bytes(void) { return static_cast<int>(sizeof(ParamSegment)); }
+int bpb_transpose_pad(const float* in, int64_t ld_in, int rows, int cols, float* out, int64_t ld_out, int out_rows,
+                      int out_cols, void* stream) {
+    return transpose_pad(in, ld_in, rows, cols, out, ld_out, out_rows, out_cols, S(stream));
+}
+
+int bpb_ce_ls_bwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c,
+                  float eps, float loss_weight, float* dlogits, int64_t ldg, void* stream) {
+    return ce_ls_bwd(logits, ld, targets, weights, n, c, eps, loss_weight, dlogits, ldg, S(stream));
+}
+int bpb_triplet_bwd(const float* emb_knd, const void* vis, int vis_mode, const float* hp, const float* hn,
+                    const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
+                    float loss_weight, float* demb_knd, void* stream) {
+    return triplet_bwd(emb_knd, vis, vis_mode, hp, hn, hp_idx, hn_idx, out4, n, k, d, margin, loss_weight, demb_knd,
+                       S(stream));
+}
+int bpb_bn1d_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* y, int64_t ld_y,
+                 const float* gamma, float eps, int m, int c, float* dx, int64_t ld_dx, int accumulate, float* dgamma,
+                 float* dbeta, void* stream) {
+    return bn1d_bwd(dy, ld_dy, x, ld_x, y, ld_y, gamma, eps, m, c, dx, ld_dx, accumulate, dgamma, dbeta, S(stream));
+}
+int bpb_colsum_f32(const float* x, int64_t ld, int m, int c, float* out, void* stream) {
+    return colsum_f32(x, ld, m, c, out, S(stream));
+}
+int bpb_head_pool_bwd_prep(float* g, const float* pooled, const float* mask_sum, int n, int c, int kp1, int hw_full,
+                           float* dms, void* stream) {
+    return head_pool_bwd_prep(g, pooled, mask_sum, n, c, kp1, hw_full, dms, S(stream));
+}
+int bpb_head_dmask(const void* x, const float* gs, int n, int q, int cb, int c_off, int ctot, int kp1, float* out,
+                   void* stream) {
+    return head_dmask(x, gs, n, q, cb, c_off, ctot, kp1, out, S(stream));
+}
+int bpb_head_pixel_bwd(const float* const* dmask_t, float* const* dlow, const int* hb, const int* wb, int nb,
+                       const float* probs, const float* dms, int n, int h, int w, int kp1, const float* target_masks,
+                       int hm, int wm, float label_smoothing, float pix_coef, const float* ext_dlogits, float* dbf,
+                       void* stream) {
+    return head_pixel_bwd(dmask_t, dlow, hb, wb, nb, probs, dms, n, h, w, kp1, target_masks, hm, wm, label_smoothing,
+                          pix_coef, ext_dlogits, dbf, S(stream));
+}
+int bpb_head_dwf(const void* x, const float* dlow, int n, int q, int cb, int c_off, int ctot, int kp1, float* dwf,
+                 void* stream) {
+    return head_dwf(x, dlow, n, q, cb, c_off, ctot, kp1, dwf, S(stream));
+}
+int bpb_pixel_fold_bwd(const float* dwf, const float* dbf, const float* w, const float* gamma, const float* scale,
+                       const float* shift, const float* mean_invstd, int kp1, int c, int64_t count, float* dw,
+                       float* db, float* dgamma, float* dbeta, float* coefab, void* stream) {
+    return pixel_fold_bwd(dwf, dbf, w, gamma, scale, shift, mean_invstd, kp1, c, count, dw, db, dgamma, dbeta, coefab,
+                          S(stream));
+}
+int bpb_head_branch_bwd(const void* x, const float* mt, const float* gs, const float* dlow, const float* wf,
+                        const float* coefab, int n, int hb, int wb, int cb, int c_off, int ctot, int h, int w, int kp1,
+                        void* dx, void* stream) {
+    return head_branch_bwd(x, mt, gs, dlow, wf, coefab, n, hb, wb, cb, c_off, ctot, h, w, kp1, dx, S(stream));
+}
+
+int bpb_l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, void* stream) {
+    return l2_normalize(x, y, rows, d, eps, S(stream));
 }
 
 }  // extern "C"

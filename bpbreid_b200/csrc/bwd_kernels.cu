@@ -1,0 +1,448 @@
+// Backward companions of the tensor-core convolutions (training step, loss.backward() at
+// torchreid/engine/image/part_based_engine.py:98-103): ReLU / residual gradient merge, train-mode BatchNorm backward
+// (two HBM passes: per-channel reductions with a fused last-block finalize, then the elementwise gradient), stem
+// weight gradient, weight (re)packing for the forward / dgrad tensor-core operands fused with the Adam update.
+// Activations and their gradients are NHWC bf16; parameter gradients fp32.
+// Reference semantics: autograd of nn.BatchNorm2d (training), nn.ReLU, residual adds and the HRNet fuse sum
+// (torchreid/models/hrnet.py:80-96,116-137,262-279); torch.optim.Adam as built by torchreid/optim/optimizer.py.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bpb {
+
+static inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+__device__ __forceinline__ void unpack8b(const uint4& u, float* f) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8b(const float* f) {
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    return o;
+}
+
+// ----------------------------------------------------------------------------------------------
+// g = (sum_s src_s) * [y > 0]        (merge of the gradients of a tensor's consumers + ReLU backward)
+// ----------------------------------------------------------------------------------------------
+struct GradSumArgs {
+    const uint4* src[4];
+    int nsrc;
+};
+
+__global__ void __launch_bounds__(256) relu_grad_sum_kernel(GradSumArgs a, const uint4* __restrict__ y,
+                                                            uint4* __restrict__ out, int64_t total) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float acc[8];
+        unpack8b(a.src[0][i], acc);
+#pragma unroll
+        for (int s = 1; s < 4; ++s) {
+            if (s < a.nsrc) {
+                float f[8];
+                unpack8b(a.src[s][i], f);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc[t] += f[t];
+            }
+        }
+        if (y != nullptr) {
+            float yy[8];
+            unpack8b(y[i], yy);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[t] = yy[t] > 0.f ? acc[t] : 0.f;
+        }
+        out[i] = pack8b(acc);
+    }
+}
+
+int relu_grad_sum(const void* const* srcs, int nsrc, const void* y, void* out, int64_t m, int c, cudaStream_t stream) {
+    BPB_CHECK(nsrc >= 1 && nsrc <= 4, "relu_grad_sum: nsrc=%d out of range", nsrc);
+    BPB_CHECK(c % 8 == 0, "relu_grad_sum: C=%d must be a multiple of 8", c);
+    GradSumArgs a{};
+    a.nsrc = nsrc;
+    for (int s = 0; s < nsrc; ++s) a.src[s] = reinterpret_cast<const uint4*>(srcs[s]);
+    const int64_t total = m * (c / 8);
+    int blocks = ceil_div(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    relu_grad_sum_kernel<<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(out),
+                                                     total);
+    BPB_LAUNCH_CHECK("relu_grad_sum_kernel");
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Train-mode BatchNorm backward.  y = gamma * xhat + beta, xhat = (raw - mean) * invstd, batch statistics.
+//   g      = dL/dy at the BN output; optionally gated by the ReLU that follows (relu_affine: raw*scale+shift > 0) and /
+//            or gathered from a 2^up-times finer map (adjoint of the nearest upsample inside the HRNet fuse sum)
+//   dbeta  = sum g ; dgamma = sum g*xhat
+//   draw   = gamma*invstd * (g - dbeta/M - xhat * dgamma/M)
+// Pass 1 (reduce) accumulates the two sums per channel (fp32 in registers -> fp64 atomics, last block finalizes into
+// coef[2][C] = {dbeta/M, dgamma/M} and the parameter gradients); pass 2 (apply) writes draw as bf16, optionally in the
+// zero-inserted 2x layout the stride-2 dgrad / wgrad consume.
+// ----------------------------------------------------------------------------------------------
+struct BnBwdArgs {
+    const uint4* dy;
+    const uint4* raw;
+    const float* mean_invstd;   // [2][C]
+    const float* scale;         // gamma * invstd  [C]
+    const float* shift;
+    int n, h, w, cvec;          // geometry of `raw`
+    int up_log2;                // dy lives on a (h << up) x (w << up) map
+    int relu_affine;
+    int c_lo;                   // parameters cover channels [c_lo, C)
+};
+
+__device__ __forceinline__ void bn_bwd_load_g(const BnBwdArgs& a, unsigned r, int cv, const float* rawf,
+                                              const float* sc, const float* sh, float* g) {
+    if (a.up_log2 == 0) {
+        unpack8b(a.dy[static_cast<size_t>(r) * a.cvec + cv], g);
+    } else {
+        const unsigned ox = r % a.w, t = r / a.w;
+        const unsigned oy = t % a.h, im = t / a.h;
+        const int f = 1 << a.up_log2;
+        const unsigned hh = a.h << a.up_log2, ww = a.w << a.up_log2;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g[q] = 0.f;
+        for (int dy = 0; dy < f; ++dy)
+            for (int dx = 0; dx < f; ++dx) {
+                float v[8];
+                unpack8b(a.dy[(static_cast<size_t>(im * hh + oy * f + dy) * ww + ox * f + dx) * a.cvec + cv], v);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g[q] += v[q];
+            }
+    }
+    if (a.relu_affine) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g[q] = (rawf[q] * sc[q] + sh[q]) > 0.f ? g[q] : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ ws,
+                                                            unsigned int* __restrict__ counter, double inv_count,
+                                                            float* __restrict__ coef, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta) {
+    const int width = a.cvec < 256 ? a.cvec : 256;
+    const int rows_per_block = 256 / width;
+    const int tx = threadIdx.x % width, ty = threadIdx.x / width;
+    const unsigned m = static_cast<unsigned>(a.n) * a.h * a.w;
+    const int c = a.cvec * 8;
+    __shared__ float red[2][256][8];
+    __shared__ int s_is_last;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    const int cv = tx;
+    if (ty < rows_per_block && cv < a.cvec) {
+        float mean[8], istd[8], sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mean[j] = a.mean_invstd[cv * 8 + j];
+            istd[j] = a.mean_invstd[c + cv * 8 + j];
+            sc[j] = a.relu_affine ? a.scale[cv * 8 + j] : 0.f;
+            sh[j] = a.relu_affine ? a.shift[cv * 8 + j] : 0.f;
+        }
+        for (unsigned r = blockIdx.x * rows_per_block + ty; r < m; r += gridDim.x * rows_per_block) {
+            float rawf[8], g[8];
+            unpack8b(a.raw[static_cast<size_t>(r) * a.cvec + cv], rawf);
+            bn_bwd_load_g(a, r, cv, rawf, sc, sh, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] += g[j];
+                q[j] += g[j] * (rawf[j] - mean[j]) * istd[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[0][threadIdx.x][j] = s[j]; red[1][threadIdx.x][j] = q[j]; }
+    __syncthreads();
+    if (ty == 0 && cv < a.cvec) {
+        for (int l = 1; l < rows_per_block; ++l)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += red[0][l * width + tx][j]; q[j] += red[1][l * width + tx][j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(ws + cv * 8 + j, static_cast<double>(s[j]));
+            atomicAdd(ws + c + cv * 8 + j, static_cast<double>(q[j]));
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_is_last) {
+        __threadfence();
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+            const double sg = __ldcg(ws + ch), sgx = __ldcg(ws + c + ch);
+            coef[ch] = static_cast<float>(sg * inv_count);
+            coef[c + ch] = static_cast<float>(sgx * inv_count);
+            const int pc = ch - a.c_lo;
+            if (pc >= 0) {
+                if (dbeta) dbeta[pc] = static_cast<float>(sg);
+                if (dgamma) dgamma[pc] = static_cast<float>(sgx);
+            }
+            ws[ch] = 0.0;
+            ws[c + ch] = 0.0;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
+                                                           uint4* __restrict__ out, int zero_insert) {
+    const int width = a.cvec < 256 ? a.cvec : 256;
+    const int rows_per_block = 256 / width;
+    const int tx = threadIdx.x % width, ty = threadIdx.x / width;
+    if (ty >= rows_per_block) return;
+    const unsigned m = static_cast<unsigned>(a.n) * a.h * a.w;
+    const int c = a.cvec * 8;
+    const int cv = tx;
+    if (cv >= a.cvec) return;
+    float mean[8], istd[8], sc[8], sh[8], c1[8], c2[8], k[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        mean[j] = a.mean_invstd[cv * 8 + j];
+        istd[j] = a.mean_invstd[c + cv * 8 + j];
+        k[j] = a.scale[cv * 8 + j];
+        sc[j] = k[j];
+        sh[j] = a.relu_affine ? a.shift[cv * 8 + j] : 0.f;
+        c1[j] = coef[cv * 8 + j];
+        c2[j] = coef[c + cv * 8 + j];
+    }
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (unsigned r = blockIdx.x * rows_per_block + ty; r < m; r += gridDim.x * rows_per_block) {
+        float rawf[8], g[8], o[8];
+        unpack8b(a.raw[static_cast<size_t>(r) * a.cvec + cv], rawf);
+        bn_bwd_load_g(a, r, cv, rawf, sc, sh, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = k[j] * (g[j] - c1[j] - (rawf[j] - mean[j]) * istd[j] * c2[j]);
+        if (!zero_insert) {
+            out[static_cast<size_t>(r) * a.cvec + cv] = pack8b(o);
+        } else {
+            const unsigned ox = r % a.w, t = r / a.w;
+            const unsigned oy = t % a.h, im = t / a.h;
+            const size_t base = (static_cast<size_t>(im * 2 * a.h + 2 * oy) * (2 * a.w) + 2 * ox) * a.cvec + cv;
+            out[base] = pack8b(o);
+            out[base + a.cvec] = zero;
+            out[base + static_cast<size_t>(2 * a.w) * a.cvec] = zero;
+            out[base + static_cast<size_t>(2 * a.w) * a.cvec + a.cvec] = zero;
+        }
+    }
+}
+
+static int bn_bwd_grid(int64_t m, int cvec) {
+    const int width = cvec < 256 ? cvec : 256;
+    int blocks = ceil_div(m, 256 / width);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    return blocks;
+}
+
+int bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
+                  int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,
+                  float* dgamma, float* dbeta, cudaStream_t stream) {
+    BPB_CHECK(c % 8 == 0 && c <= 2048, "bn_bwd_reduce: C=%d must be a multiple of 8 and <= 2048", c);
+    BPB_CHECK(up_log2 >= 0 && up_log2 <= 3, "bn_bwd_reduce: up_log2=%d", up_log2);
+    BnBwdArgs a{reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(raw), mean_invstd, scale, shift,
+                n, h, w, c / 8, up_log2, relu_affine, c_lo};
+    double* ws = reinterpret_cast<double*>(workspace);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + 2 * static_cast<size_t>(c));
+    const int64_t m = static_cast<int64_t>(n) * h * w;
+    bn_bwd_reduce_kernel<<<bn_bwd_grid(m, c / 8), 256, 0, stream>>>(a, ws, counter, 1.0 / static_cast<double>(m), coef,
+                                                                    dgamma, dbeta);
+    BPB_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+    return 0;
+}
+
+int bn_bwd_apply(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
+                 const float* coef, int n, int h, int w, int c, int up_log2, int relu_affine, int zero_insert,
+                 void* draw, cudaStream_t stream) {
+    BPB_CHECK(c % 8 == 0 && c <= 2048, "bn_bwd_apply: C=%d must be a multiple of 8 and <= 2048", c);
+    BnBwdArgs a{reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(raw), mean_invstd, scale, shift,
+                n, h, w, c / 8, up_log2, relu_affine, 0};
+    const int64_t m = static_cast<int64_t>(n) * h * w;
+    bn_bwd_apply_kernel<<<bn_bwd_grid(m, c / 8), 256, 0, stream>>>(a, coef, reinterpret_cast<uint4*>(draw), zero_insert);
+    BPB_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Stem weight gradient (3 -> 64 channels, NCHW fp32 image, PyTorch weight layout [64][3][k][k]):
+//   dW[co][ci][r][s] += sum_pix draw[pix][co] * img[n][ci][oy*stride + r - pad][ox*stride + s - pad]
+// CTA: 256 threads = 64 output channels x 4 tap groups; 64-pixel chunks staged through shared memory.
+// ----------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ img,
+                                                         const __nv_bfloat16* __restrict__ draw,
+                                                         float* __restrict__ dw, int n, int h, int wd, int stride,
+                                                         int ho, int wo) {
+    constexpr int kTaps = 3 * KS * KS;
+    constexpr int kPer = (kTaps + 3) / 4;                    // taps per thread group
+    constexpr int kPix = KS == 3 ? 64 : 32;          // pixels per staged chunk (static shared memory <= 48 KB)
+    __shared__ float s_img[kPix][kTaps + 1];
+    __shared__ float s_dy[kPix][64];
+    const int co = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    float acc[kPer];
+#pragma unroll
+    for (int t = 0; t < kPer; ++t) acc[t] = 0.f;
+    const int64_t total = static_cast<int64_t>(n) * ho * wo;
+    constexpr int pad = KS / 2;
+    for (int64_t base = static_cast<int64_t>(blockIdx.x) * kPix; base < total;
+         base += static_cast<int64_t>(gridDim.x) * kPix) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kPix * kTaps; i += 256) {
+            const int px = i / kTaps, tp = i % kTaps;
+            const int64_t pix = base + px;
+            float v = 0.f;
+            if (pix < total) {
+                const int ox = pix % wo, oy = (pix / wo) % ho, im = pix / (static_cast<int64_t>(wo) * ho);
+                const int ci = tp / (KS * KS), r = (tp / KS) % KS, sx = tp % KS;
+                const int iy = oy * stride + r - pad, ix = ox * stride + sx - pad;
+                if (iy >= 0 && iy < h && ix >= 0 && ix < wd)
+                    // the forward consumed the image at bf16 precision (stem_conv_kernel)
+                    v = __bfloat162float(__float2bfloat16(img[((static_cast<int64_t>(im) * 3 + ci) * h + iy) * wd + ix]));
+            }
+            s_img[px][tp] = v;
+        }
+        for (int i = threadIdx.x; i < kPix * 64; i += 256) {
+            const int px = i >> 6, cc = i & 63;
+            const int64_t pix = base + px;
+            s_dy[px][cc] = pix < total ? __bfloat162float(draw[pix * 64 + cc]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int px = 0; px < kPix; ++px) {
+            const float d = s_dy[px][co];
+#pragma unroll
+            for (int t = 0; t < kPer; ++t) {
+                const int tp = grp * kPer + t;
+                if (tp < kTaps) acc[t] += d * s_img[px][tp];
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kPer; ++t) {
+        const int tp = grp * kPer + t;
+        if (tp < kTaps) atomicAdd(dw + co * kTaps + tp, acc[t]);
+    }
+}
+
+int stem_wgrad(const float* img, const void* draw, float* dw, int n, int h, int wd, int cout, int ksize, int stride,
+               cudaStream_t stream) {
+    BPB_CHECK(ksize == 3 || ksize == 7, "stem_wgrad: ksize %d unsupported", ksize);
+    BPB_CHECK(cout == 64, "stem_wgrad: cout %d unsupported", cout);
+    const int pad = ksize / 2;
+    const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (wd + 2 * pad - ksize) / stride + 1;
+    const int64_t total = static_cast<int64_t>(n) * ho * wo;
+    int blocks = ceil_div(total, 64);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (ksize == 3)
+        stem_wgrad_kernel<3><<<blocks, 256, 0, stream>>>(img, reinterpret_cast<const __nv_bfloat16*>(draw), dw, n, h, wd,
+                                                         stride, ho, wo);
+    else
+        stem_wgrad_kernel<7><<<blocks, 256, 0, stream>>>(img, reinterpret_cast<const __nv_bfloat16*>(draw), dw, n, h, wd,
+                                                         stride, ho, wo);
+    BPB_LAUNCH_CHECK("stem_wgrad_kernel");
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Parameter update + operand packing over ONE flat fp32 parameter buffer.
+// Segment table (device): every parameter tensor is a segment [off, off+numel).  kind 1 = tensor-core conv weight
+// [cout][cin][k][k]: its gradient lives in the flat gradient buffer in OHWI order (what tc_wgrad_kernel writes) and
+// two bf16 operand copies are refreshed after the update -- OHWI for the forward conv and [cin][flipped taps][cout]
+// for the data gradient (which is then the forward kernel run on dY).
+// Adam: torch.optim.Adam semantics (L2 weight decay added to the gradient, bias correction, eps outside the sqrt).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_segment(const ParamSegment* __restrict__ segs, int nseg, int64_t i) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].off <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) adam_pack_kernel(const ParamSegment* __restrict__ segs, int nseg, int64_t total,
+                                                        float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, float lr,
+                                                        float beta1, float beta2, float eps, float wd, float bc1,
+                                                        float bc2, float grad_scale, int do_update) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const ParamSegment sg = segs[find_segment(segs, nseg, i)];
+        const int64_t li = i - sg.off;
+        int64_t gi = i;
+        int co = 0, ci = 0, r = 0, s = 0;
+        if (sg.kind == 1) {
+            const int kk = sg.k * sg.k;
+            co = static_cast<int>(li / (static_cast<int64_t>(sg.cin) * kk));
+            const int rem = static_cast<int>(li - static_cast<int64_t>(co) * sg.cin * kk);
+            ci = rem / kk;
+            const int tap = rem - ci * kk;
+            r = tap / sg.k; s = tap - r * sg.k;
+            gi = sg.off + (static_cast<int64_t>(co) * kk + tap) * sg.cin + ci;
+        }
+        float w = p[i];
+        if (do_update && sg.trainable) {
+            float gr = g[gi] * grad_scale + wd * w;
+            const float mm = beta1 * m[i] + (1.f - beta1) * gr;
+            const float vv = beta2 * v[i] + (1.f - beta2) * gr * gr;
+            m[i] = mm; v[i] = vv;
+            w -= lr * (mm / bc1) / (sqrtf(vv / bc2) + eps);
+            p[i] = w;
+        }
+        if (sg.kind == 1) {
+            const int kk = sg.k * sg.k;
+            const __nv_bfloat16 wb = __float2bfloat16(w);
+            const uint16_t wbits = *reinterpret_cast<const uint16_t*>(&wb);
+            if (sg.wf) sg.wf[(static_cast<int64_t>(co) * kk + r * sg.k + s) * sg.cin + ci] = wbits;
+            if (sg.wd) sg.wd[(static_cast<int64_t>(ci) * kk + (sg.k - 1 - r) * sg.k + (sg.k - 1 - s)) * sg.cout + co] = wbits;
+        }
+    }
+}
+
+int adam_pack(const void* segs, int nseg, int64_t total, float* p, const float* g, float* m, float* v, float lr,
+              float beta1, float beta2, float eps, float wd, int step, float grad_scale, int do_update,
+              cudaStream_t stream) {
+    BPB_CHECK(nseg >= 1 && total >= 1, "adam_pack: empty parameter set");
+    BPB_CHECK(!do_update || (g && m && v && step >= 1), "adam_pack: update needs g/m/v and step >= 1");
+    const float bc1 = do_update ? 1.f - powf(beta1, static_cast<float>(step)) : 1.f;
+    const float bc2 = do_update ? 1.f - powf(beta2, static_cast<float>(step)) : 1.f;
+    int blocks = ceil_div(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    adam_pack_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const ParamSegment*>(segs), nseg, total, p, g, m, v,
+                                                 lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale, do_update);
+    BPB_LAUNCH_CHECK("adam_pack_kernel");
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// out[c][r] = in[r][c] (fp32, zero padding of out's extra rows / columns): operand staging for the tf32 GEMMs of the
+// Linear-layer backward (the tensor-core kernel wants both operands K-major)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ in, int64_t ld_in, int rows,
+                                                            int cols, float* __restrict__ out, int64_t ld_out,
+                                                            int out_rows, int out_cols) {
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;    // bx over input cols, by over input rows
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int r = by + j, c = bx + tx;
+        tile[j][tx] = (r < rows && c < cols) ? in[static_cast<int64_t>(r) * ld_in + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int oc = bx + j, orow = by + tx;               // out[oc][orow]
+        if (oc < out_rows && orow < out_cols) out[static_cast<int64_t>(oc) * ld_out + orow] = tile[tx][j];
+    }
+}
+
+int transpose_pad(const float* in, int64_t ld_in, int rows, int cols, float* out, int64_t ld_out, int out_rows,
+                  int out_cols, cudaStream_t stream) {
+    BPB_CHECK(out_rows >= cols && out_cols >= rows, "transpose_pad: output smaller than the transposed input");
+    dim3 grid(ceil_div(out_rows, 32), ceil_div(out_cols, 32));
+    transpose_pad_kernel<<<grid, 256, 0, stream>>>(in, ld_in, rows, cols, out, ld_out, out_rows, out_cols);
+    BPB_LAUNCH_CHECK("transpose_pad_kernel");
+    return 0;
+}
+
+}  // namespace bpb

@@ -38,6 +38,24 @@ int check_cuda(cudaError_t e, const char* what);
         if (::bpb::check_cuda(cudaGetLastError(), name)) return 3; \
     } while (0)
 
+// Per-DEVICE (not per-process) one-time kernel attribute setup: cudaFuncSetAttribute applies to the current device
+// only, and a DataParallel-style host drives several devices from one process (SURVEY.md section 8b "Threading").
+// Idempotent, so the benign race between two host threads costs at most a redundant call.
+#define BPB_SET_MAX_SMEM(kern, bytes)                                                                       \
+    do {                                                                                                    \
+        static unsigned long long bpb_done_[2] = {0ull, 0ull};                                              \
+        int bpb_dev_ = 0;                                                                                   \
+        BPB_CUDA(cudaGetDevice(&bpb_dev_));                                                                 \
+        const int bpb_w_ = (bpb_dev_ >> 6) & 1;                                                             \
+        if (!((bpb_done_[bpb_w_] >> (bpb_dev_ & 63)) & 1ull)) {                                             \
+            BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            bpb_done_[bpb_w_] |= 1ull << (bpb_dev_ & 63);                                                   \
+        }                                                                                                   \
+    } while (0)
+
+// SM count of the CURRENT device (cached per device), 0 on error (bpb::set_error holds the message)
+int device_sm_count();
+
 // Encodes a tiled tensor map (driver entry point fetched at run time: no link dependency on libcuda).
 // dims/strides are innermost-first; strides_bytes has rank-1 entries (stride of dim 1..rank-1).
 int make_tensor_map(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int rank,

@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kDThreads, 1) part_distance_tc_kernel(const __
                             else if (kVis == VIS_FLOAT) w = sqrtf(qw * gw_p[u]);
                             const float pd_out = (kVis == VIS_BOOL && w == 0.f) ? -1.f : dv;
                             o[e] = pd_out;
-                            if (jc + u < a.ng) local_max = fmaxf(local_max, pd_out);
+                            if (row_ok && jc + u < a.ng) local_max = fmaxf(local_max, pd_out);
                             if (kMax) num[u] = fmaxf(num[u], kVis == VIS_NONE ? dv : pd_out);
                             else num[u] += dv * w;
                         }
@@ -515,7 +515,9 @@ int part_distance(const float* qf, const float* gf, const void* qv, const void* 
     BPB_CHECK(metric == METRIC_EUCLIDEAN || metric == METRIC_COSINE, "part_distance: unknown metric %d", metric);
     BPB_CHECK(strat == STRAT_MEAN || strat == STRAT_MAX, "part_distance: unknown strategy %d", strat);
     BPB_CHECK(p >= 1 && p <= 32, "part_distance: P=%d out of range", p);
-    BPB_CHECK(!(vis_mode == VIS_FLOAT && strat == STRAT_MAX), "part_distance: 'max' needs boolean visibility");
+    // continuous visibility scores always take the weighted mean in the reference, whatever dist_combine_strat says
+    // (distance.py:181-219 never looks at it)
+    if (vis_mode == VIS_FLOAT) strat = STRAT_MEAN;
     float* qs = scratch + 4;
     float* gs = qs + static_cast<int64_t>(p) * nq;
     uint32_t* qmask = reinterpret_cast<uint32_t*>(gs + static_cast<int64_t>(p) * ng);
@@ -552,24 +554,16 @@ int part_distance(const float* qf, const float* gf, const void* qv, const void* 
         const int tiles_q = ceil_div(nq, kDM), tiles_g = ceil_div(ng, kDN);
         DistParams a{nq, ng, p, d, vis_mode, metric, strat, qv, gv, qs, gs, qmask, gmask, dist, part_dist, scratch,
                      tiles_q, tiles_g, tiles_q * tiles_g};
-        static int num_sms = 0;
-        if (num_sms == 0) {
-            int dev = 0;
-            BPB_CUDA(cudaGetDevice(&dev));
-            BPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        }
+        const int num_sms = device_sm_count();
+    if (num_sms <= 0) return 2;
         const size_t smem = kDStages * kDStageBytes + 1024 + (2 * p + 1) * kDN * 4;
         const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
         const bool eu = metric == METRIC_EUCLIDEAN, mx = strat == STRAT_MAX;
 #define BPB_DIST_LAUNCH(VIS, EU, MX)                                                                              \
     do {                                                                                                          \
-        static bool configured = false;                                                                           \
-        if (!configured) {                                                                                        \
-            BPB_CUDA(cudaFuncSetAttribute(part_distance_tc_kernel<VIS, EU, MX>,                                   \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDSmemMax));          \
-            configured = true;                                                                                    \
-        }                                                                                                         \
-        part_distance_tc_kernel<VIS, EU, MX><<<grid, kDThreads, smem, stream>>>(tmQ, tmG, a);                     \
+        auto kern = part_distance_tc_kernel<VIS, EU, MX>;                                                         \
+        BPB_SET_MAX_SMEM(kern, kDSmemMax);                                                                        \
+        kern<<<grid, kDThreads, smem, stream>>>(tmQ, tmG, a);                                                     \
     } while (0)
 #define BPB_DIST_VIS(VIS)                                                                                         \
     do {                                                                                                          \

@@ -134,11 +134,7 @@ int pixel_classify(const void* feats, const float* wf, const float* bf, int n, i
 #define BPB_PC_CASE(K)                                                                                              \
     case K: {                                                                                                       \
         auto kern = pixel_classify_kernel<K>;                                                                       \
-        static bool configured = false;                                                                             \
-        if (!configured) {                                                                                          \
-            BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));          \
-            configured = true;                                                                                      \
-        }                                                                                                           \
+        BPB_SET_MAX_SMEM(kern, 160 * 1024);                                                                                                           \
         kern<<<blocks, 256, smem, stream>>>(reinterpret_cast<const uint4*>(feats), wf, bf, n, hw, c, logits_nchw,   \
                                             probs, fg_mask, vis_bits, vis_cont);                                    \
         break;                                                                                                      \
@@ -250,11 +246,7 @@ int part_pool(const void* feats, const float* probs, const float* fg_mask, int n
 #define BPB_PP_CASE(JJ)                                                                                         \
     case JJ: {                                                                                                  \
         auto kern = part_pool_kernel<JJ>;                                                                       \
-        static bool configured = false;                                                                         \
-        if (!configured) {                                                                                      \
-            BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));      \
-            configured = true;                                                                                  \
-        }                                                                                                       \
+        BPB_SET_MAX_SMEM(kern, 200 * 1024);                                                                                                       \
         kern<<<grid, 128, smem, stream>>>(reinterpret_cast<const uint4*>(feats), probs, fg_mask, n, hw, c, pooled); \
         break;                                                                                                  \
     }

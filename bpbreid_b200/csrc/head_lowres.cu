@@ -138,11 +138,7 @@ int head_branch_stats(const void* x, int n, int hb, int wb, int cb, int h, int w
     const size_t smem = direct ? 0 : static_cast<size_t>(hb) * wb * 8 * sizeof(uint4);
     BPB_CHECK(smem <= 160 * 1024, "head_branch_stats: branch map %dx%d too large for shared memory", hb, wb);
     BPB_CHECK(direct || (hb <= 64 && wb <= 64), "head_branch_stats: low-resolution branch %dx%d larger than 64", hb, wb);
-    static bool configured = false;
-    if (!configured) {
-        BPB_CUDA(cudaFuncSetAttribute(branch_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
-    }
+    BPB_SET_MAX_SMEM(branch_stats_kernel, 160 * 1024);
     dim3 grid(n, cb / 64);
     branch_stats_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const uint4*>(x), hb, wb, cb, h, w, partial, c_off,
                                                      ctot);
@@ -210,11 +206,7 @@ int head_lowres_logits(const void* x, const float* wf, int64_t rows, int cb, int
 #define BPB_LL_CASE(K)                                                                                         \
     case K: {                                                                                                  \
         auto kern = lowres_logits_kernel<K>;                                                                   \
-        static bool configured = false;                                                                        \
-        if (!configured) {                                                                                     \
-            BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));     \
-            configured = true;                                                                                 \
-        }                                                                                                      \
+        BPB_SET_MAX_SMEM(kern, 100 * 1024);                                                                                                      \
         kern<<<blocks, 256, smem, stream>>>(reinterpret_cast<const uint4*>(x), wf, rows, cb, c_off, ctot, out); \
         break;                                                                                                 \
     }
@@ -371,11 +363,7 @@ int head_pixel(const float* const* lowres_logits, float* const* mask_t, const in
 #define BPB_PH_CASE(K)                                                                                         \
     case K: {                                                                                                  \
         auto kern = pixel_head_kernel<K>;                                                                      \
-        static bool configured = false;                                                                        \
-        if (!configured) {                                                                                     \
-            BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));     \
-            configured = true;                                                                                 \
-        }                                                                                                      \
+        BPB_SET_MAX_SMEM(kern, 160 * 1024);                                                                                                      \
         kern<<<n, 256, smem, stream>>>(g, bf, h, w, logits, probs, fg_mask, vis_bits, vis_cont, mask_sum);      \
         break;                                                                                                 \
     }
@@ -492,11 +480,7 @@ int head_branch_pool(const void* x, const float* mt, const float* mask_sum, int 
 #define BPB_BP_CASE(JJ)                                                                                        \
     case JJ: {                                                                                                 \
         auto kern = branch_pool_kernel<JJ>;                                                                    \
-        static bool configured = false;                                                                        \
-        if (!configured) {                                                                                     \
-            BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));     \
-            configured = true;                                                                                 \
-        }                                                                                                      \
+        BPB_SET_MAX_SMEM(kern, 200 * 1024);                                                                                                      \
         kern<<<grid, 128, smem, stream>>>(reinterpret_cast<const uint4*>(x), mt, mask_sum, n, q, cb, c_off, ctot, \
                                           inv_hw, pooled);                                                     \
         break;                                                                                                 \

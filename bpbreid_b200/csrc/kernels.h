@@ -15,14 +15,14 @@ struct BnFuse {
     float* scale; float* shift;
     float eps, momentum;
     int c_lo;                   // parameters cover channels [c_lo, cout) (IBN: first half is instance-normalised)
+    float* save_mean_invstd;    // optional [2][cout]: batch mean and 1/sqrt(var+eps) for the backward pass
 };
 int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                  int ksize, int stride, int bn_hint, const BnFuse* bn, cudaStream_t stream);
 int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bias, float* out, int m, int n, int k,
                    int ldo, int a_mode, int a_parts, cudaStream_t stream);
-int conv3x3_halo_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, const BnFuse* bn,
-                      cudaStream_t stream);
 int conv_num_mtiles(int n, int ho, int wo);
+bool conv_tiling(int ho, int wo, int* bh_out, int* bnimg_out);
 
 // ---- nn_kernels.cu ----------------------------------------------------------------------------
 int conv_ref(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize, int stride,
@@ -34,7 +34,7 @@ int colstats_bf16(const void* x, float* partials, int m, int c, int* tiles_out, 
 int colstats_tiles(int m);
 int bn_finalize(const float* partials, int tiles, int c, int c_lo, int64_t count, const float* gamma,
                 const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* scale,
-                float* shift, cudaStream_t stream);
+                float* shift, float* save_mean_invstd, cudaStream_t stream);
 int bn_eval_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                  float eps, int c, float* scale, float* shift, cudaStream_t stream);
 int bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* res_scale,
@@ -97,5 +97,66 @@ int rank_market1501(const float* dist, const int64_t* q_pids, const int64_t* g_p
                     int* first_rank, float* cmc, double* map_out, int64_t* num_valid, float* map32_out,
                     int* overflow_flag, cudaStream_t stream);
 int argsort_rows(const float* dist, int nq, int ng, int32_t* indices, cudaStream_t stream);
+
+// ---- tc_wgrad.cu ------------------------------------------------------------------------------
+int conv_wgrad_tc(const void* x, const void* dy, float* dw, int n, int h, int wd, int cin, int cout, int ksize,
+                  int stride, int dy_up, cudaStream_t stream);
+
+// ---- bwd_kernels.cu ---------------------------------------------------------------------------
+// one parameter tensor inside the flat fp32 parameter buffer (device table consumed by adam_pack)
+struct ParamSegment {
+    int64_t off, numel;
+    int kind;                   // 0: plain tensor, 1: tensor-core conv weight [cout][cin][k][k]
+    int trainable;
+    int cout, cin, k, pad_;
+    uint16_t* wf;               // bf16 OHWI copy (forward operand) or null
+    uint16_t* wd;               // bf16 [cin][flipped taps][cout] copy (dgrad operand) or null
+};
+int relu_grad_sum(const void* const* srcs, int nsrc, const void* y, void* out, int64_t m, int c, cudaStream_t stream);
+int bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
+                  int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,
+                  float* dgamma, float* dbeta, cudaStream_t stream);
+int bn_bwd_apply(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
+                 const float* coef, int n, int h, int w, int c, int up_log2, int relu_affine, int zero_insert,
+                 void* draw, cudaStream_t stream);
+int stem_wgrad(const float* img, const void* draw, float* dw, int n, int h, int wd, int cout, int ksize, int stride,
+               cudaStream_t stream);
+int adam_pack(const void* segs, int nseg, int64_t total, float* p, const float* g, float* m, float* v, float lr,
+              float beta1, float beta2, float eps, float wd, int step, float grad_scale, int do_update,
+              cudaStream_t stream);
+int transpose_pad(const float* in, int64_t ld_in, int rows, int cols, float* out, int64_t ld_out, int out_rows,
+                  int out_cols, cudaStream_t stream);
+
+// ---- loss_bwd.cu ------------------------------------------------------------------------------
+int ce_ls_bwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c, float eps,
+              float loss_weight, float* dlogits, int64_t ldg, cudaStream_t stream);
+int triplet_bwd(const float* emb_knd, const void* vis, int vis_mode, const float* hp, const float* hn,
+                const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
+                float loss_weight, float* demb_knd, cudaStream_t stream);
+int bn1d_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* y, int64_t ld_y,
+             const float* gamma, float eps, int m, int c, float* dx, int64_t ld_dx, int accumulate, float* dgamma,
+             float* dbeta, cudaStream_t stream);
+int colsum_f32(const float* x, int64_t ld, int m, int c, float* out, cudaStream_t stream);
+
+// ---- head_bwd.cu ------------------------------------------------------------------------------
+int head_pool_bwd_prep(float* g, const float* pooled, const float* mask_sum, int n, int c, int kp1, int hw_full,
+                       float* dms, cudaStream_t stream);
+int head_dmask(const void* x, const float* gs, int n, int q, int cb, int c_off, int ctot, int kp1, float* out,
+               cudaStream_t stream);
+int head_pixel_bwd(const float* const* dmask_t, float* const* dlow, const int* hb, const int* wb, int nb,
+                   const float* probs, const float* dms, int n, int h, int w, int kp1, const float* target_masks,
+                   int hm, int wm, float label_smoothing, float pix_coef, const float* ext_dlogits, float* dbf,
+                   cudaStream_t stream);
+int head_dwf(const void* x, const float* dlow, int n, int q, int cb, int c_off, int ctot, int kp1, float* dwf,
+             cudaStream_t stream);
+int pixel_fold_bwd(const float* dwf, const float* dbf, const float* w, const float* gamma, const float* scale,
+                   const float* shift, const float* mean_invstd, int kp1, int c, int64_t count, float* dw, float* db,
+                   float* dgamma, float* dbeta, float* coefab, cudaStream_t stream);
+int head_branch_bwd(const void* x, const float* mt, const float* gs, const float* dlow, const float* wf,
+                    const float* coefab, int n, int hb, int wb, int cb, int c_off, int ctot, int h, int w, int kp1,
+                    void* dx, cudaStream_t stream);
+
+// ---- eval_kernels.cu --------------------------------------------------------------------------
+int l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, cudaStream_t stream);
 
 }  // namespace bpb

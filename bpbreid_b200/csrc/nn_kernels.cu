@@ -172,11 +172,7 @@ int stem_conv(const float* img, const float* w, void* y, float* partials, int n,
         stem_conv_kernel<3><<<grid, 128, smem, stream>>>(img, w, reinterpret_cast<__nv_bfloat16*>(y), partials, n, h, wd,
                                                          stride, ho, wo);
     } else {
-        static bool configured = false;
-        if (!configured) {
-            BPB_CUDA(cudaFuncSetAttribute(stem_conv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            configured = true;
-        }
+        BPB_SET_MAX_SMEM(stem_conv_kernel<7>, 64 * 1024);
         stem_conv_kernel<7><<<grid, 128, smem, stream>>>(img, w, reinterpret_cast<__nv_bfloat16*>(y), partials, n, h, wd,
                                                          stride, ho, wo);
     }
@@ -245,7 +241,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
                                                           const float* gamma, const float* beta, float eps,
                                                           float momentum,
                                                           float* running_mean, float* running_var, float* scale,
-                                                          float* shift) {
+                                                          float* shift, float* save) {
     const int cl = threadIdx.x & 31, j = threadIdx.x >> 5;
     const int ch = blockIdx.x * 32 + cl;
     __shared__ double rs[8][32], rq[8][32];
@@ -266,9 +262,11 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
         // parameters cover channels [c_lo, c) only (IBN: the first c_lo channels are instance-normalised elsewhere)
         const int pc = ch - c_lo;
         const float g = (gamma && pc >= 0) ? gamma[pc] : 1.f, b = (beta && pc >= 0) ? beta[pc] : 0.f;
-        const float sc = g * rsqrtf(static_cast<float>(var) + eps);
+        const float istd = rsqrtf(static_cast<float>(var) + eps);
+        const float sc = g * istd;
         scale[ch] = sc;
         shift[ch] = b - static_cast<float>(mean) * sc;
+        if (save) { save[ch] = static_cast<float>(mean); save[c + ch] = istd; }
         if (running_mean && pc >= 0)
             running_mean[pc] = (1.f - momentum) * running_mean[pc] + momentum * static_cast<float>(mean);
         if (running_var && pc >= 0)
@@ -278,11 +276,11 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
 
 int bn_finalize(const float* partials, int tiles, int c, int c_lo, int64_t count, const float* gamma,
                 const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* scale,
-                float* shift, cudaStream_t stream) {
+                float* shift, float* save_mean_invstd, cudaStream_t stream) {
     const double inv = 1.0 / static_cast<double>(count);
     const double unbias = count > 1 ? static_cast<double>(count) / static_cast<double>(count - 1) : 1.0;
     bn_finalize_kernel<<<ceil_div(c, 32), 256, 0, stream>>>(partials, tiles, c, c_lo, inv, unbias, gamma, beta, eps, momentum,
-                                                            running_mean, running_var, scale, shift);
+                                                            running_mean, running_var, scale, shift, save_mean_invstd);
     BPB_LAUNCH_CHECK("bn_finalize_kernel");
     return 0;
 }

@@ -257,11 +257,7 @@ int argsort_rows(const float* dist, int nq, int ng, int32_t* indices, cudaStream
     while (npow2 < ng) npow2 <<= 1;
     BPB_CHECK(npow2 <= 16384, "argsort_rows: Ng=%d exceeds the 16384-entry shared-memory sorter", ng);
     const size_t smem = static_cast<size_t>(npow2) * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        BPB_CUDA(cudaFuncSetAttribute(argsort_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        configured = true;
-    }
+    BPB_SET_MAX_SMEM(argsort_rows_kernel, 128 * 1024);
     argsort_rows_kernel<<<nq, 1024, smem, stream>>>(dist, ng, npow2, indices);
     BPB_LAUNCH_CHECK("argsort_rows_kernel");
     return 0;

@@ -41,6 +41,11 @@ struct GemmParams {
     int rshift_bytes;   // mode 3: bytes between vertically adjacent taps inside the A stage (Wo * row_bytes)
     int kwrap;      // elements after which the A channel coordinate wraps (cin for conv, K for matrix, D for parts)
     int ksize, stride, pad, Ho, Wo;
+    // conv output tiling: a 128-row tile = bnimg images x bh rows x full width.  Tile t covers rows [hb*bh, hb*bh+bh)
+    // of images [g*bnimg, g*bnimg+bnimg) with g = t / tpg, hb = t % tpg; tile row r is output pixel
+    // (n0 + (r >> chunk_log2)) * hw + h0*Wo + (r & (chunk-1)), chunk = bh*Wo (a power of two dividing 128).
+    // Matrix modes: tpg = 0 (rows are simply m0 + r).
+    int tpg, bnimg, bh, chunk_log2, hw, nimg;
     int ldo;        // output leading dimension (elements)
     void* out;
     float* stats;   // optional [m_tiles, 2, N] per-tile column sum / sum of squares (EPI_RAW_STATS)
@@ -53,6 +58,7 @@ struct GemmParams {
     const float* gamma; const float* beta;
     float* running_mean; float* running_var;
     float* scale; float* shift;
+    float* save;    // optional [2][N]: batch mean / 1/sqrt(var+eps) (consumed by the BatchNorm backward)
     float eps, momentum;
     double inv_count, unbias;
     int c_lo;
@@ -83,7 +89,7 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
     const int b_tap_bytes = BN * p.row_bytes;
     const int stage_bytes = a_bytes + taps * b_tap_bytes;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int m_tiles = (p.M + kTileM - 1) / kTileM;
+    const int m_tiles = p.tpg == 0 ? (p.M + kTileM - 1) / kTileM : ((p.nimg + p.bnimg - 1) / p.bnimg) * p.tpg;
     const int total_tiles = m_tiles * n_tiles;
     constexpr int kPitch = BN * 2 + 16;                        // epilogue staging tile row pitch (bytes)
     uint8_t* epi_tile = smem + p.stages * stage_bytes;         // [128][kPitch], RAW_STATS only
@@ -137,10 +143,9 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
                 const int m_tile = t / n_tiles, n_tile = t - m_tile * n_tiles;
                 int n0 = 0, hbase = 0;
                 if (p.mode == 0 || p.mode == 3) {
-                    const int hw = p.Ho * p.Wo;
-                    const int p0 = m_tile * kTileM;
-                    n0 = p0 / hw;
-                    hbase = ((p0 - n0 * hw) / p.Wo) * p.stride - p.pad;
+                    const int grp = m_tile / p.tpg;
+                    n0 = grp * p.bnimg;
+                    hbase = (m_tile - grp * p.tpg) * p.bh * p.stride - p.pad;
                 }
                 const int m0 = m_tile * kTileM, nb0 = n_tile * BN;
                 int tap_r = 0, tap_s = 0, kc = 0, bk = 0, part = 0;
@@ -228,8 +233,19 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int m_tile = t / n_tiles, n_tile = t % n_tiles;
             const uint32_t buf = lt & 1, use = lt >> 1;
-            const int m0 = m_tile * kTileM, c_base = n_tile * BN;
-            const int valid_rows = min(kTileM, p.M - m0);
+            const int c_base = n_tile * BN;
+            // first output row of the tile and how many of its 128 rows exist (always a prefix: rows are image-major)
+            int m0, valid_rows;
+            if (p.tpg == 0) {
+                m0 = m_tile * kTileM;
+                valid_rows = min(kTileM, p.M - m0);
+            } else {
+                const int grp = m_tile / p.tpg;
+                const int n0 = grp * p.bnimg;
+                m0 = n0 * p.hw + (m_tile - grp * p.tpg) * p.bh * p.Wo;
+                valid_rows = min(kTileM, (p.nimg - n0) << p.chunk_log2);
+            }
+            const int cmask = (1 << p.chunk_log2) - 1;
             mbar_wait_a(accf_a + buf * 8, use & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * W * BN;
@@ -253,7 +269,8 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
                         mbar_arrive_a(acce_a + buf * 8);
                     }
                     if (row < valid_rows) {
-                        float* dst = out + static_cast<size_t>(m0 + row) * p.ldo + c_base + c0;
+                        float* dst = out + static_cast<size_t>(m0 + (row >> p.chunk_log2) * p.hw + (row & cmask)) * p.ldo +
+                                     c_base + c0;
                         if (c_base + c0 + 32 <= p.N) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -316,7 +333,8 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
                         const int r = ch / kChunksPerRow, cc = ch % kChunksPerRow;
                         if (r < valid_rows) {
                             const uint4 o = *reinterpret_cast<const uint4*>(epi_tile + r * kPitch + cc * 16);
-                            *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + r) * p.ldo + c_base + cc * 8) = o;
+                            *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + (r >> p.chunk_log2) * p.hw + (r & cmask)) *
+                                                                p.ldo + c_base + cc * 8) = o;
                         }
                     }
                 }
@@ -381,9 +399,11 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
                         const int pc = ch - p.c_lo;
                         const float g = (p.gamma && pc >= 0) ? p.gamma[pc] : 1.f;
                         const float b = (p.beta && pc >= 0) ? p.beta[pc] : 0.f;
-                        const float sc = g * rsqrtf(static_cast<float>(var) + p.eps);
+                        const float istd = rsqrtf(static_cast<float>(var) + p.eps);
+                        const float sc = g * istd;
                         p.scale[ch] = sc;
                         p.shift[ch] = b - static_cast<float>(mean) * sc;
+                        if (p.save) { p.save[ch] = static_cast<float>(mean); p.save[p.N + ch] = istd; }
                         if (p.running_mean && pc >= 0)
                             p.running_mean[pc] = (1.f - p.momentum) * p.running_mean[pc] + p.momentum * static_cast<float>(mean);
                         if (p.running_var && pc >= 0)
@@ -417,12 +437,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + epi + 1024;
     BPB_CHECK(smem <= 200 * 1024, "tc_gemm: %zu bytes of shared memory requested", smem);
     auto kern = tc_gemm_kernel<BN, kTf32, kEpi>;
-    static bool configured = false;
-    if (!configured) {
-        BPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
-    const int total = ((p.M + kTileM - 1) / kTileM) * ((p.N + BN - 1) / BN);
+    BPB_SET_MAX_SMEM(kern, 200 * 1024);
+    const int m_tiles_l = p.tpg == 0 ? (p.M + kTileM - 1) / kTileM : ((p.nimg + p.bnimg - 1) / p.bnimg) * p.tpg;
+    const int total = m_tiles_l * ((p.N + BN - 1) / BN);
     // persistent: exactly as many CTAs as are co-resident (registers / smem via the occupancy API, TMEM: 2*BN
     // columns each) -- a static tile assignment must never have a second wave of CTAs
     // (shared memory is the binding limit: 56 registers x 192 threads allow 6 CTAs; the occupancy API under-reports
@@ -433,17 +450,24 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     if (per_sm > 2048 / threads) per_sm = 2048 / threads;
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        BPB_CUDA(cudaGetDevice(&dev));
-        BPB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int num_sms = device_sm_count();
+    if (num_sms <= 0) return 2;
     int grid = num_sms * per_sm;
     if (grid > total) grid = total;
     kern<<<grid, threads, smem, stream>>>(tmA, tmB, p);
     BPB_LAUNCH_CHECK("tc_gemm_kernel");
     return 0;
+}
+
+// 128 output pixels = bnimg images x bh rows x the full output width: bh = the largest divisor of ho whose bh*wo
+// divides 128 (384x128 inputs: the 24x8 map tiles as 2 images x 8 rows, the 12x4 map as 8 images x 4 rows).
+bool conv_tiling(int ho, int wo, int* bh_out, int* bnimg_out) {
+    if (wo < 1 || wo > 128 || 128 % wo) return false;
+    int bh = 128 / wo < ho ? 128 / wo : ho;
+    while (bh > 1 && (ho % bh || 128 % (bh * wo))) --bh;
+    *bh_out = bh;
+    *bnimg_out = 128 / (bh * wo);
+    return true;
 }
 
 static int pick_stages(int stage_bytes, int budget_bytes) {
@@ -472,8 +496,7 @@ static void choose_issue_config(GemmParams& p, int bn_tile, int taps, int epi_by
     // first pass: every MMA warp gets two ring slots (prefetch distance); second pass: one slot each
     // (a first pass that demanded two slots per warp was measured slower: it trades CTAs per SM for ring depth)
     for (int slots_per_warp = 1; slots_per_warp >= 1 && best_issuers == 0; --slots_per_warp) {
-        static const int w_env = [] { const char* e = getenv("BPB_CONV_MAX_W"); return e ? atoi(e) : 0; }();   // tuning hook
-        const int w_cap = w_env > 0 ? w_env : max_w;
+        const int w_cap = max_w;
         for (int w = (w_cap < kMaxMmaWarps ? w_cap : kMaxMmaWarps); w >= 1; --w) {
             if (p.k_iters % w) continue;
             const int cols = pow2_cols(2 * w * bn_tile);
@@ -515,19 +538,8 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (wd + 2 * pad - ksize) / stride + 1;
     BPB_CHECK(cin % 32 == 0 && cout % 32 == 0, "conv_bf16_tc: channels must be multiples of 32 (cin=%d cout=%d)", cin,
               cout);
-    // bn_hint bit 10: run narrow 3x3 stride-1 layers from one halo tile per output tile (tc_conv_halo.cu).  Opt-in:
-    // it cuts the L2 -> SM operand stream 2.5x but was measured SLOWER than the row-shift schedule (44 vs 39 us for
-    // the C=32 layer, 13.0 vs 12.5 ms per step) -- the bound is the per-tile latency chain, not L2 bandwidth.
-    if (ksize == 3 && stride == 1 && stats == nullptr && (bn_hint & 0x400) != 0) {
-        const int rc = conv3x3_halo_bf16(x, w, y, n, h, wd, cin, cout, bn, stream);
-        if (rc >= 0) return rc;
-    }
-    bn_hint &= ~0x400;
-    BPB_CHECK(wo <= 128 && 128 % wo == 0, "conv_bf16_tc: output width %d must divide 128", wo);
-    const int bh = (128 / wo) < ho ? (128 / wo) : ho;
-    BPB_CHECK(ho % bh == 0, "conv_bf16_tc: output height %d not a multiple of tile rows %d", ho, bh);
-    const int bnimg = 128 / (wo * bh);
-    BPB_CHECK(bnimg * wo * bh == 128, "conv_bf16_tc: tile does not cover 128 pixels (ho=%d wo=%d)", ho, wo);
+    int bh = 0, bnimg = 0;
+    BPB_CHECK(conv_tiling(ho, wo, &bh, &bnimg), "conv_bf16_tc: output width %d must divide 128", wo);
     // row-shift mode: 3x3 stride-1, tile inside one image, vertical tap offset = whole swizzle atoms (Wo % 8 == 0)
     const bool rowshift = ksize == 3 && stride == 1 && bnimg == 1 && (wo % 8) == 0 && (bn_hint & 0x100) == 0;
     bn_hint &= 0xFF;
@@ -552,6 +564,9 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
     p.out = y;
     p.stats = stats;
     p.bias = nullptr;
+    p.tpg = ho / bh; p.bnimg = bnimg; p.bh = bh; p.hw = ho * wo; p.nimg = n;
+    p.chunk_log2 = 0;
+    while ((1 << p.chunk_log2) < bh * wo) ++p.chunk_log2;
     p.mode = rowshift ? 3 : 0;
     p.a_rows = rowshift ? kTileM + 2 * wo : kTileM;
     p.rshift_bytes = rowshift ? wo * p.row_bytes : 0;
@@ -563,12 +578,13 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
         p.gamma = bn->gamma; p.beta = bn->beta;
         p.running_mean = bn->running_mean; p.running_var = bn->running_var;
         p.scale = bn->scale; p.shift = bn->shift;
+        p.save = bn->save_mean_invstd;
         p.eps = bn->eps; p.momentum = bn->momentum;
         p.inv_count = 1.0 / static_cast<double>(p.M);
         p.unbias = p.M > 1 ? static_cast<double>(p.M) / static_cast<double>(p.M - 1) : 1.0;
         p.c_lo = bn->c_lo;
     }
-    const int m_tiles = (p.M + kTileM - 1) / kTileM;
+    const int m_tiles = conv_num_mtiles(n, ho, wo);
     int bn_tile = pick_bn(m_tiles, cout, bn_hint);
     if (bn_hint == 0 && ksize == 3 && bn_tile > 64) bn_tile = 64;       // narrow tiles + several issuers beat one N=128 issuer
     // Layers with many tiles (>= 4096: the stride-4 maps at batch 256) run faster as three CTAs per SM with ONE MMA
@@ -610,16 +626,20 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
 // read as the concatenation over parts (bpbreid.py:212 concat_parts_embeddings) without materialising it.
 int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bias, float* out, int m, int n, int k,
                    int ldo, int a_mode, int a_parts, cudaStream_t stream) {
-    BPB_CHECK(k % 32 == 0, "linear_tf32_tc: K=%d must be a multiple of 32", k);
+    // K need not be a multiple of the 32-float chunk in the row-major mode: the tensor maps carry the true K, so the
+    // tail of the last chunk is TMA zero fill on both operands (the Linear backward contracts over the batch rows)
+    BPB_CHECK(k >= 1 && (a_mode == 0 || k % 32 == 0), "linear_tf32_tc: K=%d must be a multiple of 32 in part mode", k);
+    BPB_CHECK(k % 4 == 0, "linear_tf32_tc: K=%d must be a multiple of 4 (16-byte rows of W)", k);
     BPB_CHECK(ldo % 4 == 0 && ldo >= n, "linear_tf32_tc: ldo=%d must be >= N and a multiple of 4", ldo);
     GemmParams p{};
     p.M = m; p.N = n;
-    p.kc = 32; p.kchunks = k / 32; p.k_iters = p.kchunks; p.cin = k;
+    p.kc = 32; p.kchunks = (k + 31) / 32; p.k_iters = p.kchunks; p.cin = k;
     p.row_bytes = 128;
     p.kwrap = k;
     p.a_rows = kTileM; p.rshift_bytes = 0;
     p.mode = a_mode == 0 ? 1 : 2; p.ksize = 1; p.stride = 1; p.pad = 0; p.Ho = 0; p.Wo = 0;
     p.dchunks = 1;
+    p.tpg = 0; p.bnimg = 1; p.bh = 0; p.chunk_log2 = 7; p.hw = 0; p.nimg = 0;
     p.ldo = ldo; p.out = out; p.stats = nullptr; p.bias = bias;
     const int m_tiles = (m + kTileM - 1) / kTileM;
     int bn = n >= 128 ? 128 : (n >= 64 ? 64 : 32);
@@ -662,6 +682,10 @@ int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bia
     return 0;
 }
 
-int conv_num_mtiles(int n, int ho, int wo) { return (n * ho * wo + kTileM - 1) / kTileM; }
+int conv_num_mtiles(int n, int ho, int wo) {
+    int bh = 0, bnimg = 0;
+    if (!conv_tiling(ho, wo, &bh, &bnimg)) return (n * ho * wo + kTileM - 1) / kTileM;
+    return ((n + bnimg - 1) / bnimg) * (ho / bh);
+}
 
 }  // namespace bpb

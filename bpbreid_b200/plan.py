@@ -47,13 +47,9 @@ class Lazy:
 
 
 def _tc_tileable(cin, cout, ho, wo):
-    """Shapes the tcgen05 tiler accepts: 128 output pixels = (images) x (rows) x (full output width)."""
-    if cin % 32 or cout % 32 or wo > 128 or 128 % wo:
-        return False
-    bh = min(ho, 128 // wo)
-    if ho % bh:
-        return False
-    return (128 // (wo * bh)) * wo * bh == 128
+    """Shapes the tcgen05 tiler accepts: 128 output pixels = (images) x (rows) x (full output width); the rows per
+    tile are the largest divisor of ho that keeps the tile at 128 pixels (tc_gemm.cu: conv_tiling)."""
+    return not (cin % 32 or cout % 32 or wo > 128 or 128 % wo)
 
 
 class ForwardPlan:

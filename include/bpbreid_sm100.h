@@ -32,8 +32,7 @@ int bpb_abi_version(void);
 int bpb_conv_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                   int ksize, int stride, int bn_hint, void* stream);
 /* bn_hint: 0 = automatic tile width; 32/64/128 forces the N tile; bit 8 (0x100) forces the one-tap-per-stage schedule
- * for 3x3 stride-1 layers; bit 10 (0x400) opts in to the single-halo-tile schedule (csrc/tc_conv_halo.cu; Cout 32/64,
- * no per-tile `stats`).  The bits only select between numerically equivalent schedules (test / tuning hooks). */
+ * for 3x3 stride-1 layers.  The bits only select between numerically equivalent schedules (test hooks). */
 int bpb_conv_num_mtiles(int n, int ho, int wo);
 /* Same convolution with the train-mode BatchNorm that follows it fused into the launch (conv + nn.BatchNorm2d call
  * pairs, e.g. hrnet.py:82-83): every CTA adds its per-channel sums to `bn_workspace` (fp64 atomics) and the last CTA
@@ -43,7 +42,8 @@ int bpb_conv_num_mtiles(int n, int ho, int wo);
 int bpb_conv_bn_bf16(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
                      int ksize, int stride, int bn_hint, void* bn_workspace, const float* gamma, const float* beta,
                      float eps, float momentum, float* running_mean, float* running_var, int c_lo, float* scale,
-                     float* shift, void* stream);
+                     float* shift, float* save_mean_invstd, void* stream);
+/* save_mean_invstd: optional [2][cout] fp32 -- batch mean and 1/sqrt(var + eps), kept for bpb_bn_bwd_*. */
 int64_t bpb_conv_bn_workspace_bytes(int cout);
 /* SIMT reference convolution, same operands (validation / shapes the tensor-core tiler rejects). */
 int bpb_conv_ref_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize,
@@ -62,7 +62,7 @@ int bpb_colstats_tiles(int m);
  * Replaces the nn.BatchNorm2d call sites of hrnet.py:73,77,106-111 etc. in training mode. */
 int bpb_bn_finalize(const float* partials, int tiles, int c, int c_lo, int64_t count, const float* gamma,
                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                    float* scale, float* shift, void* stream);
+                    float* scale, float* shift, float* save_mean_invstd, void* stream);
 /* eval mode: scale/shift from the running statistics. */
 int bpb_bn_eval_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                      float eps, int c, float* scale, float* shift, void* stream);
@@ -172,6 +172,95 @@ int bpb_rank_market1501(const float* dist, const int64_t* q_pids, const int64_t*
                         int* overflow_flag, void* stream);
 /* Stable ascending argsort of every row (== np.argsort(kind='stable')); ng <= 16384. */
 int bpb_argsort_rows(const float* dist, int nq, int ng, int32_t* indices, void* stream);
+
+/* ---- training backward: replaces autograd's `loss.backward()` + `optimizer.step()` for this path
+ *      (torchreid/engine/image/part_based_engine.py:98-103) ---------------------------------------------------- */
+
+/* Weight gradient of the NHWC bf16 convolution on the tcgen05 tensor cores (both operands MN-major: the pixel axis
+ * is the contraction axis, no transposition pass).  dw [cout, ksize*ksize, cin] fp32 is ACCUMULATED (red.add): zero it
+ * per step.  dy is the gradient w.r.t. the raw conv output, [n, ho, wo, cout] bf16, or with dy_up = 1 the
+ * zero-inserted [n, 2ho, 2wo, cout] layout produced by bpb_bn_bwd_apply(zero_insert = 1) for stride-2 layers.
+ * The DATA gradient needs no entry point of its own: it is bpb_conv_bf16 run on dy (zero-inserted for stride 2)
+ * with the [cin][flipped taps][cout] weight copy that bpb_adam_pack maintains, ksize taps, stride 1.
+ * Replaces: autograd of nn.Conv2d at hrnet.py:60-64,80-96,116-137,222-257,459-483; resnet.py:43-63,128-154. */
+int bpb_conv_wgrad_bf16(const void* x, const void* dy, float* dw, int n, int h, int wd, int cin, int cout, int ksize,
+                        int stride, int dy_up, void* stream);
+/* out = (sum of up to 4 bf16 [m, c] gradient tensors) * [y > 0]   (y NULL: plain sum).  Merges the gradients of a
+ * tensor's consumers and applies the backward of the ReLU that produced it (hrnet.py:92-96,133-137,277). */
+int bpb_relu_grad_sum(const void* const* srcs, int nsrc, const void* y, void* out, int64_t m, int c, void* stream);
+/* Train-mode BatchNorm2d backward in two passes over raw [n,h,w,c] bf16 (the conv output the forward normalised):
+ * reduce -> coef[2][c] = {sum g / M, sum g*xhat / M}, dgamma/dbeta [c - c_lo] (written, fp32);
+ * apply  -> draw = scale * (g - coef0 - xhat * coef1) as bf16, compact or zero-inserted (stride-2 producers).
+ * g is dy, optionally gated by the following ReLU (relu_affine: raw*scale+shift > 0) and, with up_log2 > 0, summed over
+ * the 2^up x 2^up block of the finer map dy lives on (adjoint of the nearest upsample of hrnet.py:239-241).
+ * workspace: bpb_bn_bwd_workspace_bytes(c) bytes, zero-initialised once (left zeroed by every call). */
+int64_t bpb_bn_bwd_workspace_bytes(int c);
+int bpb_bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
+                      int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,
+                      float* dgamma, float* dbeta, void* stream);
+int bpb_bn_bwd_apply(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
+                     const float* coef, int n, int h, int w, int c, int up_log2, int relu_affine, int zero_insert,
+                     void* draw, void* stream);
+/* Weight gradient of the stem convolution (NCHW fp32 image, PyTorch [64,3,k,k] layout, accumulated). */
+int bpb_stem_wgrad(const float* img, const void* draw, float* dw, int n, int h, int wd, int cout, int ksize, int stride,
+                   void* stream);
+/* torch.optim.Adam step (torchreid/optim/optimizer.py:96-103: L2 weight decay) over ONE flat fp32 parameter buffer +
+ * refresh of the bf16 tensor-core operand copies of every conv weight.  `segs`: device array of nseg records of
+ * bpb_param_segment_bytes() bytes {int64 off, int64 numel, int32 kind, trainable, cout, cin, k, pad, void* wf, void* wd};
+ * kind 1 = conv weight whose gradient is stored OHWI (as bpb_conv_wgrad_bf16 writes it).  do_update = 0: pack only. */
+int bpb_adam_pack(const void* segs, int nseg, int64_t total, float* p, const float* g, float* m, float* v, float lr,
+                  float beta1, float beta2, float eps, float wd, int step, float grad_scale, int do_update,
+                  void* stream);
+int bpb_param_segment_bytes(void);
+/* out[c][r] = in[r][c] with zero padding up to [out_rows, out_cols]: operand staging for the tf32 GEMMs of the
+ * nn.Linear backward (bpbreid.py:324-350, 398-415). */
+int bpb_transpose_pad(const float* in, int64_t ld_in, int rows, int cols, float* out, int64_t ld_out, int out_rows,
+                      int out_cols, void* stream);
+
+/* Loss gradients.  dlogits [n, ldg] = coef_i (softmax - smoothed target), coef_i = loss_weight/n or
+ * loss_weight * w_i / max(sum|w|, 1e-12) (cross_entropy_loss.py:34-56); columns >= c are not touched. */
+int bpb_ce_ls_bwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c,
+                  float eps, float loss_weight, float* dlogits, int64_t ldg, void* stream);
+/* demb [K, N, D] += gradient of loss_weight * (part-averaged batch-hard triplet) through the mined pairs recorded by
+ * bpb_triplet_fwd (hp/hn/hp_idx/hn_idx/out4); exact-zero distances carry no gradient
+ * (part_averaged_triplet_loss.py:88-91, 95-195). */
+int bpb_triplet_bwd(const float* emb_knd, const void* vis, int vis_mode, const float* hp, const float* hn,
+                    const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
+                    float loss_weight, float* demb_knd, void* stream);
+/* Train-mode nn.BatchNorm1d backward on fp32 [m, c] (bpbreid.py:336-338, 404-409); y != NULL gates by the following
+ * ReLU (y = the layer output); dx is written or accumulated; dgamma / dbeta optional. */
+int bpb_bn1d_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* y, int64_t ld_y,
+                 const float* gamma, float eps, int m, int c, float* dx, int64_t ld_dx, int accumulate, float* dgamma,
+                 float* dbeta, void* stream);
+int bpb_colsum_f32(const float* x, int64_t ld, int m, int c, float* out, void* stream);
+/* Backward of the branch-map head (forward: bpb_head_branch_stats .. bpb_head_branch_pool), see csrc/head_bwd.cu:
+ * pool_bwd_prep scales g = dL/dpooled [K+3, n, c] in place by the pooling norm and emits d(mask sums) [n, K+3];
+ * dmask: out[n, q, K+3] = <g[j, n, c_off:], x[n, q, :]>;  pixel_bwd: per image mask/softmax backward (+ the
+ * body-part attention loss when target_masks != NULL, coefficient pix_coef = weight / (n*h*w)) -> low-resolution
+ * logit gradients dlow[b] [n*q_b, K+1], dbf [K+1] +=;  dwf [K+1, ctot] += dlow^T x;  fold_bwd: parameter gradients of
+ * PixelToPartClassifier (bpbreid.py:376-385) + the batch-statistics coefficients coefab [2][ctot];
+ * branch_bwd: dx[b] (bf16, same shape as the branch map). */
+int bpb_head_pool_bwd_prep(float* g, const float* pooled, const float* mask_sum, int n, int c, int kp1, int hw_full,
+                           float* dms, void* stream);
+int bpb_head_dmask(const void* x, const float* gs, int n, int q, int cb, int c_off, int ctot, int kp1, float* out,
+                   void* stream);
+int bpb_head_pixel_bwd(const float* const* dmask_t, float* const* dlow, const int* hb, const int* wb, int nb,
+                       const float* probs, const float* dms, int n, int h, int w, int kp1, const float* target_masks,
+                       int hm, int wm, float label_smoothing, float pix_coef, const float* ext_dlogits, float* dbf,
+                       void* stream);
+int bpb_head_dwf(const void* x, const float* dlow, int n, int q, int cb, int c_off, int ctot, int kp1, float* dwf,
+                 void* stream);
+int bpb_pixel_fold_bwd(const float* dwf, const float* dbf, const float* w, const float* gamma, const float* scale,
+                       const float* shift, const float* mean_invstd, int kp1, int c, int64_t count, float* dw,
+                       float* db, float* dgamma, float* dbeta, float* coefab, void* stream);
+int bpb_head_branch_bwd(const void* x, const float* mt, const float* gs, const float* dlow, const float* wf,
+                        const float* coefab, int n, int hb, int wb, int cb, int c_off, int ctot, int h, int w, int kp1,
+                        void* dx, void* stream);
+
+/* y[r, :] = x[r, :] / max(|x[r, :]|_2, eps) for `rows` rows of d floats (in place allowed).
+ * Replaces Engine.normalize = F.normalize(p=2, dim=-1) (torchreid/engine/engine.py:558-559), applied to the
+ * [N, P, D] test embeddings at torchreid/engine/image/part_based_engine.py:205-208. */
+int bpb_l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     assert set(_lib._SIGS) | {"bpb_last_error", "bpb_abi_version"} == set(syms)
     loaded = _lib.load()
-    assert loaded.bpb_abi_version() == 1
+    assert loaded.bpb_abi_version() == 2
 
 
 def test_model_builder_api_and_errors():
@@ -64,4 +64,8 @@ def test_planner_tiling_rule():
     from bpbreid_b200.plan import _tc_tileable
     assert _tc_tileable(32, 32, 64, 32) and _tc_tileable(256, 256, 8, 4) and _tc_tileable(64, 64, 16, 8)
     assert not _tc_tileable(3, 64, 128, 64)
-    assert not _tc_tileable(128, 128, 24, 8)         # 384x128 inputs: 192 px/img does not tile by 128
+    # 384x128 inputs: the 24x8 / 12x4 maps tile as (images x rows x width) = 2x8x8 / 8x4x4 (tc_gemm.cu conv_tiling)
+    assert _tc_tileable(128, 128, 24, 8) and _tc_tileable(256, 256, 12, 4) and _tc_tileable(32, 32, 96, 32)
+    assert not _tc_tileable(64, 64, 10, 12)          # width must divide 128
+    assert _lib.query("bpb_conv_num_mtiles", 4, 24, 8) == 2 * 3 and _lib.query("bpb_conv_num_mtiles", 11, 12, 4) == 2 * 3
+    assert _lib.query("bpb_conv_num_mtiles", 256, 64, 32) == 256 * 16

@@ -23,7 +23,7 @@ for (n, h, w, cin, cout, k, st) in SHAPES:
     sc, sh = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
     call = lambda: _lib.call("bpb_conv_bn_bf16", x.data_ptr(), wt.data_ptr(), y.data_ptr(), None, n, h, w, cin, cout, k, st, 0,
                              ws.data_ptr(), g.data_ptr(), b.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(), 0,
-                             sc.data_ptr(), sh.data_ptr(), s)
+                             sc.data_ptr(), sh.data_ptr(), None, s)
     for _ in range(2):
         call()
     ts = []
