@@ -62,6 +62,7 @@ _SIGS = {
     "bpb_stem_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bpb_adam_pack": [_P, _I, _L, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _I, _P],
     "bpb_param_segment_bytes": [],
+    "bpb_memset_zero": [_P, _L, _P],
     "bpb_transpose_pad": [_P, _L, _I, _I, _P, _L, _I, _I, _P],
     "bpb_ce_ls_bwd": [_P, _L, _P, _P, _I, _I, _F, _F, _P, _L, _P],
     "bpb_triplet_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _P],
@@ -74,7 +75,8 @@ _SIGS = {
     "bpb_pixel_fold_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _P, _P, _P, _P, _P, _P],
     "bpb_head_branch_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
 }
-_PLAIN_INT = {"bpb_conv_num_mtiles", "bpb_colstats_tiles", "bpb_abi_version", "bpb_stem_conv_tiles"}
+_PLAIN_INT = {"bpb_conv_num_mtiles", "bpb_colstats_tiles", "bpb_abi_version", "bpb_stem_conv_tiles",
+              "bpb_param_segment_bytes"}
 
 
 def header_symbols():

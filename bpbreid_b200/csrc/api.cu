@@ -264,6 +264,10 @@ int bpb_adam_pack(const void* segs, int nseg, int64_t total, float* p, const flo
                   void* stream) {
     return adam_pack(segs, nseg, total, p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale, do_update, S(stream));
 }
+int bpb_memset_zero(void* p, int64_t bytes, void* stream) {
+    BPB_CUDA(cudaMemsetAsync(p, 0, static_cast<size_t>(bytes), S(stream)));
+    return 0;
+}
 int bpb_param_segment_bytes(void) { return static_cast<int>(sizeof(ParamSegment)); }
 int bpb_transpose_pad(const float* in, int64_t ld_in, int rows, int cols, float* out, int64_t ld_out, int out_rows,
                       int out_cols, void* stream) {

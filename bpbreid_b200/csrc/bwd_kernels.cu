@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(const ParamSegment* __re
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const ParamSegment sg = segs[find_segment(segs, nseg, i)];
         const int64_t li = i - sg.off;
+        if (li >= sg.numel) continue;                          // alignment padding between segments
         int64_t gi = i;
         int co = 0, ci = 0, r = 0, s = 0;
         if (sg.kind == 1) {

@@ -121,6 +121,7 @@ class BPBreID(nn.Module):
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
         self.invalidate_plans()
+        self._param_version = getattr(self, "_param_version", 0) + 1      # training plans re-pack their operand copies
         return out
 
 

@@ -39,11 +39,13 @@ class Act:
 
 
 class Lazy:
-    """Raw conv output + the BN scale/shift that still has to be applied to it."""
-    __slots__ = ("raw", "scale", "shift")
+    """Raw conv output + the BN scale/shift that still has to be applied to it.  In gradient mode it also remembers
+    how it was produced (conv module, its input, the BN module, saved batch mean / invstd) for the backward pass."""
+    __slots__ = ("raw", "scale", "shift", "conv", "x_in", "bn", "save", "kind")
 
-    def __init__(self, raw, scale, shift):
+    def __init__(self, raw, scale, shift, conv=None, x_in=None, bn=None, save=None, kind="tc"):
         self.raw, self.scale, self.shift = raw, scale, shift
+        self.conv, self.x_in, self.bn, self.save, self.kind = conv, x_in, bn, save, kind
 
 
 def _tc_tileable(cin, cout, ho, wo):
@@ -53,8 +55,14 @@ def _tc_tileable(cin, cout, ho, wo):
 
 
 class ForwardPlan:
-    def __init__(self, model, n, h, w, training, device, conv_impl="tc", use_graph=False, debug=False):
+    def __init__(self, model, n, h, w, training, device, conv_impl="tc", use_graph=False, debug=False, grad=False,
+                 flat=None):
         self.model = model
+        # gradient mode (bpbreid_b200.train): every activation stays alive for the backward pass, BatchNorm layers
+        # save their batch mean / invstd, conv weights come from the flat parameter store's bf16 operand copies
+        self.grad = bool(grad)
+        self.flat = flat
+        self.tape = []
         self.n, self.h, self.w = n, h, w
         self.training = bool(training)
         self.device = device
@@ -121,7 +129,7 @@ class ForwardPlan:
             mine = self._scopes.pop()
             kept_ids = {id(a.buf) for a in keep}
             for buf in mine:
-                if self.debug or id(buf) in kept_ids:
+                if self.debug or self.grad or id(buf) in kept_ids:
                     self._scopes[-1].append(buf)
                 else:
                     self._free.setdefault((self._buf_lane[id(buf)], buf.numel()), []).append(buf)
@@ -177,6 +185,8 @@ class ForwardPlan:
     # ------------------------------------------------------------------ weights
     def pack_conv(self, conv: nn.Conv2d):
         key = id(conv)
+        if self.flat is not None:
+            return self.flat.forward_operand(conv)
         if key not in self._packed:
             w = conv.weight.detach()
             self._packed[key] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
@@ -198,9 +208,11 @@ class ForwardPlan:
         """partials -> (scale, shift) for nn.BatchNorm2d `bn` (train: batch stats, eval: running stats)."""
         scale, shift = self._small((c,)), self._small((c,))
         g, b, rm, rv, mom = self._bn_params(bn)
+        self._last_save = self._small((2, c)) if (self.grad and self.training) else None
         if self.training:
             self._op("bpb_bn_finalize", stats.data_ptr(), tiles, c, c_lo, count, g.data_ptr(), b.data_ptr(),
-                     BN_EPS, float(mom), rm.data_ptr(), rv.data_ptr(), scale.data_ptr(), shift.data_ptr())
+                     BN_EPS, float(mom), rm.data_ptr(), rv.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                     _lib.ptr(self._last_save))
         else:
             # inference: running statistics are constants -> folded once, outside the replayed step
             assert c_lo == 0
@@ -248,12 +260,16 @@ class ForwardPlan:
             ws = torch.zeros(_lib.query("bpb_conv_bn_workspace_bytes", cout), dtype=torch.uint8, device=self.device)
             self.persistent.append(ws)
             scale, shift = self._small((cout,)), self._small((cout,))
+            save = self._small((2, cout)) if self.grad else None
             mom = bn.momentum if bn.momentum is not None else 0.1
             self._op("bpb_conv_bn_bf16", x.t.data_ptr(), wp.data_ptr(), y.t.data_ptr(), None, x.n, x.h, x.w, x.c, cout,
                      k, s, 0, ws.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), BN_EPS, float(mom),
-                     bn.running_mean.data_ptr(), bn.running_var.data_ptr(), c_lo, scale.data_ptr(), shift.data_ptr())
-            return Lazy(y, scale, shift)
+                     bn.running_mean.data_ptr(), bn.running_var.data_ptr(), c_lo, scale.data_ptr(), shift.data_ptr(),
+                     _lib.ptr(save))
+            return Lazy(y, scale, shift, conv, x, bn, save, "tc")
         y, stats, tiles = self.conv_raw(x, conv)
+        if self.grad and self.training:
+            raise NotImplementedError(f"training backward needs the tensor-core conv path (shape {x.h}x{x.w}x{x.c}->{cout})")
         if c_lo == 0:
             scale, shift = self.bn_scale_shift(stats, tiles, y.c, y.m, bn)
         else:
@@ -262,7 +278,7 @@ class ForwardPlan:
                 mom = bn.momentum if bn.momentum is not None else 0.1
                 self._op("bpb_bn_finalize", stats.data_ptr(), tiles, y.c, c_lo, y.m, bn.weight.data_ptr(),
                          bn.bias.data_ptr(), BN_EPS, float(mom), bn.running_mean.data_ptr(),
-                         bn.running_var.data_ptr(), scale.data_ptr(), shift.data_ptr())
+                         bn.running_var.data_ptr(), scale.data_ptr(), shift.data_ptr(), None)
             else:
                 self._setup_op("bpb_bn_eval_fold", bn.weight.data_ptr(), bn.bias.data_ptr(),
                                bn.running_mean.data_ptr(), bn.running_var.data_ptr(), BN_EPS, y.c - c_lo,
@@ -347,7 +363,9 @@ class ForwardPlan:
         self._op("bpb_stem_conv", self.images.data_ptr(), wt.data_ptr(), raw.t.data_ptr(), _lib.ptr(stats), n, h, w,
                  conv.out_channels, ksize, stride)
         scale, shift = self.bn_scale_shift(stats, tiles, raw.c, raw.m, bn)
-        y = self.apply(Lazy(raw, scale, shift), True)
+        lz = Lazy(raw, scale, shift, conv, None, bn, self._last_save, "stem")
+        self._stem_geom = (ksize, stride)
+        y = self.apply(lz, True)
         self._trace("stem", [conv, bn], [], [y], ksize=ksize, stride=stride)
         return y
 
@@ -513,9 +531,10 @@ class ForwardPlan:
             self.join()
             bn = pc.bn
             mom = bn.momentum if bn.momentum is not None else 0.1
+            self.pix_save = self._small((2, ctot)) if self.grad else None
             self._op("bpb_bn_finalize", partial.data_ptr(), n, ctot, 0, n * h * w, bn.weight.data_ptr(),
                      bn.bias.data_ptr(), BN_EPS, float(mom), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
-                     scale.data_ptr(), shift.data_ptr())
+                     scale.data_ptr(), shift.data_ptr(), _lib.ptr(self.pix_save))
         else:
             self._setup_op("bpb_bn_eval_fold", pc.bn.weight.data_ptr(), pc.bn.bias.data_ptr(),
                            pc.bn.running_mean.data_ptr(), pc.bn.running_var.data_ptr(), BN_EPS, ctot,
@@ -548,6 +567,7 @@ class ForwardPlan:
                 self._op("bpb_head_branch_pool", b.t.data_ptr(), mt.data_ptr(), self.mask_sum.data_ptr(), n, b.h * b.w,
                          b.c, off, ctot, kp1, h * w, self.pooled.data_ptr())
         self.join()
+        self.hf = dict(br=br, offs=offs, ctot=ctot, scale=scale, shift=shift, wf=wf, bf=bf, lows=lows, mts=mts, h=h, w=w)
         return ctot
 
     def build_head_back(self, c):
@@ -558,6 +578,7 @@ class ForwardPlan:
         ld = (ncls + 3) // 4 * 4
         # dim reduce: Linear(C->D) + BN1d + ReLU for {global, fg, bg, parts (K*N rows jointly)}
         lin = self._small((J * n, D))
+        self.lin = lin
         self.emb = self._small((J * n, D))
         groups = [(m.global_after_pooling_dim_reduce, 0, n), (m.foreground_after_pooling_dim_reduce, n, n),
                   (m.background_after_pooling_dim_reduce, 2 * n, n), (m.parts_after_pooling_dim_reduce, 3 * n, K * n)]
@@ -682,6 +703,11 @@ class ForwardPlan:
             main.wait_stream(streams[l])
 
     def run(self, images):
+        ver = getattr(self.model, "_param_version", 0)
+        if ver != getattr(self, "_seen_version", 0):          # an optimizer step changed the fp32 masters
+            self._seen_version = ver
+            if self.flat is None:
+                self.refresh_weights()
         self.images.copy_(images, non_blocking=True)
         if self._need_setup:
             self._run_list(self.setup_ops)

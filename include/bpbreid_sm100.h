@@ -212,6 +212,8 @@ int bpb_adam_pack(const void* segs, int nseg, int64_t total, float* p, const flo
                   float beta1, float beta2, float eps, float wd, int step, float grad_scale, int do_update,
                   void* stream);
 int bpb_param_segment_bytes(void);
+/* cudaMemsetAsync(p, 0, bytes) as a recordable launch (gradient accumulators are zeroed per step). */
+int bpb_memset_zero(void* p, int64_t bytes, void* stream);
 /* out[c][r] = in[r][c] with zero padding up to [out_rows, out_cols]: operand staging for the tf32 GEMMs of the
  * nn.Linear backward (bpbreid.py:324-350, 398-415). */
 int bpb_transpose_pad(const float* in, int64_t ld_in, int rows, int cols, float* out, int64_t ld_out, int out_rows,

@@ -114,8 +114,8 @@ def gen_rank(ref):
     print("rank.npz", len(out))
 
 
-def gen_models(ref):
-    for name in MODEL_CASES:
+def gen_models(ref, only=None):
+    for name in (only or MODEL_CASES):
         c = model_case(name)
         m = ref_loader.build_reference_model(c["backbone"], c["K"], c["num_classes"])
         missing = m.load_state_dict(c["state_dict"], strict=True)
@@ -145,10 +145,49 @@ def gen_models(ref):
         print(f"model_{name}.npz", len(out))
 
 
+GRAD_FULL_KEYS = ("pixel_classifier.classifier.weight", "pixel_classifier.classifier.bias", "pixel_classifier.bn.weight",
+                  "pixel_classifier.bn.bias", "global_identity_classifier.bn.weight",
+                  "backbone_appearance_feature_extractor.conv1.weight", "backbone_appearance_feature_extractor.bn1.weight",
+                  "backbone_appearance_feature_extractor.stage4.2.branches.0.3.conv2.weight",
+                  "backbone_appearance_feature_extractor.stage2.0.fuse_layers.1.0.0.0.weight",
+                  "backbone_appearance_feature_extractor.stage3.1.fuse_layers.0.2.0.weight",
+                  "backbone_appearance_feature_extractor.incre_modules.3.0.conv3.weight",
+                  "backbone_appearance_feature_extractor.layer1.0.downsample.0.weight",
+                  "parts_after_pooling_dim_reduce.layers.0.bias", "parts_after_pooling_dim_reduce.layers.1.weight")
+
+
+def gen_grads(ref, name="hrnet32_k5_ctr", bpa_weight=0.35):
+    """Reference `loss.backward()` (part_based_engine.py:98-103) on the contractive HRNet case: GiLt (default weights)
+    + 0.35 * body-part attention loss.  Stores every parameter's gradient L2 norm and a few full tensors."""
+    c = model_case(name)
+    m = ref_loader.build_reference_model(c["backbone"], c["K"], c["num_classes"])
+    m.load_state_dict(c["state_dict"], strict=True)
+    m.train()
+    masks = torch.from_numpy(c["masks"])
+    emb, vis, ids, pix, feats, pm = m(torch.from_numpy(c["images"]), external_parts_masks=masks)
+    g = ref.GiLtLoss(None, use_visibility_scores=False, triplet_margin=0.3, loss_name="part_averaged_triplet_loss",
+                     writer=ref_loader.NoOpWriter())
+    pids = torch.from_numpy(c["pids"])
+    loss, _ = g(emb, vis, ids, pids)
+    tm = torch.nn.functional.interpolate(masks, pix.shape[2:], mode="bilinear", align_corners=True)
+    bpa = ref.BodyPartAttentionLoss(loss_type="cl", label_smoothing=0.1)
+    l2, _ = bpa(pix, tm.argmax(1))
+    total = loss + bpa_weight * l2
+    total.backward()
+    out = {"loss": t2n(total), "gilt": t2n(loss), "bpa": t2n(l2)}
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            out[f"norm/{k}"] = np.float64(p.grad.double().norm().item())
+            if k in GRAD_FULL_KEYS:
+                out[f"full/{k}"] = t2n(p.grad)
+    np.savez_compressed(os.path.join(OUT, f"grads_{name}.npz"), **out)
+    print(f"grads_{name}.npz", len(out), float(total))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
-    which = sys.argv[1:] or ["losses", "distance", "rank", "models"]
+    which = sys.argv[1:] or ["losses", "distance", "rank", "models", "grads"]
     if "losses" in which:
         gen_losses(ref)
     if "distance" in which:
@@ -157,3 +196,8 @@ if __name__ == "__main__":
         gen_rank(ref)
     if "models" in which:
         gen_models(ref)
+    only = [w.split(":", 1)[1] for w in which if w.startswith("models:")]
+    if only:
+        gen_models(ref, only)
+    if "grads" in which:
+        gen_grads(ref)

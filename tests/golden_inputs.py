@@ -112,8 +112,26 @@ def rank_case(name):
                 q_camids=q_cam.astype(np.int64), g_camids=g_cam.astype(np.int64), max_rank=max_rank)
 
 
-MODEL_CASES = ["hrnet32_k5", "resnet50_k5", "ibn_k8"]
-_MODEL_SPECS = {"hrnet32_k5": ("hrnet32", 5, 100), "resnet50_k5": ("resnet50", 5, 200), "ibn_k8": ("fastreid_resnet_ibn", 8, 300)}
+MODEL_CASES = ["hrnet32_k5", "resnet50_k5", "ibn_k8", "hrnet32_k5_384", "hrnet32_k5_ctr"]
+# name -> (backbone, K, seed, H, W, contractive)
+_MODEL_SPECS = {"hrnet32_k5": ("hrnet32", 5, 100, 256, 128, False), "resnet50_k5": ("resnet50", 5, 200, 256, 128, False),
+                "ibn_k8": ("fastreid_resnet_ibn", 8, 300, 256, 128, False),
+                # the reference's shipped input size (configs/bpbreid/*.yaml:5-6, BASELINE config 2)
+                "hrnet32_k5_384": ("hrnet32", 5, 400, 384, 128, False),
+                # "contractive" weights: the BatchNorm that closes every residual branch has gamma ~ 0.15, so each block is
+                # a small perturbation of the identity and bf16 rounding noise is NOT amplified block after block; this
+                # makes end-to-end TRAIN-mode comparisons (batch statistics) and end-to-end gradients well conditioned
+                "hrnet32_k5_ctr": ("hrnet32", 5, 500, 256, 128, True)}
+
+
+def contractive(sd):
+    out = dict(sd)
+    for k, v in sd.items():
+        if k.endswith("bn2.weight") and ".branches." in k:
+            out[k] = v * 0.15
+        elif k.endswith("bn3.weight"):
+            out[k] = v * 0.15
+    return out
 
 
 class _Cfg(dict):
@@ -146,12 +164,17 @@ def build_product_model(backbone, K, num_classes=751, **over):
                               config=make_cfg(backbone, K, **over))
 
 
-def model_case(name, n=4, h=256, w=128, num_classes=751):
+def model_case(name, n=4, num_classes=751):
     from bpbreid_b200 import params
-    backbone, K, seed = _MODEL_SPECS[name]
+    backbone, K, seed, h, w, ctr = _MODEL_SPECS[name]
     m = build_product_model(backbone, K, num_classes)
     sd = params.seeded_state_dict(m, seed)
+    if ctr:
+        sd = contractive(sd)
     g = torch.Generator().manual_seed(seed + 1)
     images = torch.randn(n, 3, h, w, generator=g).numpy()
     pids = (np.arange(n) // 2).astype(np.int64)
-    return dict(backbone=backbone, K=K, num_classes=num_classes, state_dict=sd, images=images, pids=pids, model=m)
+    # external part masks [N, K+1, H/8, W/8] (rows sum to 1, like AddBackgroundMask's softmax, mask_transform.py:81-84)
+    masks = torch.softmax(3 * torch.randn(n, K + 1, h // 8, w // 8, generator=g), 1).numpy()
+    return dict(backbone=backbone, K=K, num_classes=num_classes, state_dict=sd, images=images, pids=pids, model=m,
+                masks=masks)
