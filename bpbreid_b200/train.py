@@ -143,6 +143,7 @@ class TrainPlan(ForwardPlan):
         self._gfree = {}
         self._gref = {}
         self.bwd_ws = {}
+        self.btrace = []               # debug: one record per conv+BN backward (teacher-forced kernel checks in tests)
         super().__init__(model, n, h, w, True, device, "tc", False, debug, grad=True, flat=flat)
 
     # ------------------------------------------------------------------ gradient bookkeeping
@@ -197,6 +198,9 @@ class TrainPlan(ForwardPlan):
                   lz.shift.data_ptr(), coef.data_ptr(), raw.n, raw.h, raw.w, raw.c, up, relu_affine, zero_ins,
                   draw.t.data_ptr())
         k = conv.kernel_size[0]
+        if self.debug:
+            self.btrace.append(dict(lz=lz, dy=dy, relu_affine=relu_affine, up=up, draw=draw, zero_ins=zero_ins, dx=None,
+                                    name=self._names.get(id(conv), "?")))
         if lz.kind == "stem":
             self._bop("bpb_stem_wgrad", self.images.data_ptr(), draw.t.data_ptr(), fl.grad_ptr(conv.weight), self.n,
                       self.h, self.w, conv.out_channels, k, stride)
@@ -212,6 +216,8 @@ class TrainPlan(ForwardPlan):
         # data gradient = the forward tensor-core conv on dY with the flipped / transposed weight copy, stride 1
         self._bop("bpb_conv_bf16", draw.t.data_ptr(), wd.data_ptr(), dx.t.data_ptr(), None, draw.n, draw.h, draw.w,
                   cout, cin, k, 1, 0)
+        if self.debug:
+            self.btrace[-1]["dx"] = dx
         self.g_add(x, dx)
 
     # ------------------------------------------------------------------ taped building blocks
@@ -423,6 +429,7 @@ class TrainStep:
         self.bpa_weight = float(bpa_weight)
         self.use_graph = use_graph
         self.group = group
+        self.debug = False               # keep per-layer backward records (plan.btrace) for the kernel parity tests
         self.flat = None
         self.plans = {}
         self.graphs = {}
@@ -444,7 +451,7 @@ class TrainStep:
         cfg = dict(weights=lw, bpa_weight=self.bpa_weight if masks is not None else 0.0, bpa_label_smoothing=0.1,
                    bpa_masks=None if masks is None else torch.zeros_like(masks, dtype=torch.float32, device=dev))
         self.model.train()
-        plan = TrainPlan(self.model, n, h, w, dev, self.flat, cfg)
+        plan = TrainPlan(self.model, n, h, w, dev, self.flat, cfg, debug=self.debug)
         plan.masks_buf = cfg["bpa_masks"]
         self._build_loss(plan, lw)
         plan.build_backward()

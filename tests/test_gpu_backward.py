@@ -1,0 +1,390 @@
+"""GPU (B200): parity of the analytic backward pass (training step) through the C ABI.
+
+Checkers: plain fp32 PyTorch evaluations of the same operands for the individual kernels (tensor-core wgrad / dgrad,
+BatchNorm backward, Adam), and torch autograd over the CPU oracle restatements (oracle/model_oracle.py +
+oracle/loss_oracle_torch.py, pinned to the reference's own loss.backward() by tests/golden/grads_hrnet32_k5_ctr.npz)
+for the whole training step.  Tolerances: fp32 kernels 1e-3, bf16 operands / outputs 1e-2 (north_star)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from bpbreid_b200 import _lib, losses, train
+from tests import golden_inputs as GI
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def relmax(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-20))
+
+
+WGRAD_SHAPES = [
+    # n, h, w, cin, cout, k, s
+    (4, 64, 32, 32, 32, 3, 1), (4, 32, 16, 64, 64, 3, 1), (4, 16, 8, 128, 128, 3, 1), (8, 8, 4, 256, 256, 3, 1),
+    (3, 8, 4, 256, 256, 3, 1), (4, 64, 32, 64, 256, 1, 1), (4, 64, 32, 256, 64, 1, 1), (4, 64, 32, 256, 32, 3, 1),
+    (4, 64, 32, 256, 64, 3, 2), (4, 128, 64, 64, 64, 3, 2), (4, 64, 32, 32, 32, 3, 2), (4, 32, 16, 64, 32, 1, 1),
+    (4, 16, 8, 128, 32, 1, 1), (5, 24, 8, 128, 128, 3, 1), (11, 12, 4, 256, 256, 3, 1), (4, 8, 4, 256, 1024, 1, 1),
+    (2, 16, 8, 512, 512, 3, 1),
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD_SHAPES, ids=[str(s) for s in WGRAD_SHAPES])
+def test_conv_wgrad_tc(shape):
+    """dW = sum_pixels dY^T X on the tensor cores with MN-major operands; stride-2 layers read the zero-inserted dY."""
+    n, h, w, cin, cout, k, s = shape
+    g = torch.Generator().manual_seed(hash(shape) % 997)
+    pad = k // 2
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).to(DEV)
+    dy = torch.randn(n, ho, wo, cout, generator=g).to(torch.bfloat16).to(DEV)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, k, k), dy.float().permute(0, 3, 1, 2),
+                                      stride=s, padding=pad)
+    ref = ref.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+    for up in ([0, 1] if s == 2 else [0]):
+        dw = torch.zeros(cout, k * k, cin, device=DEV)
+        if up:
+            dyu = torch.zeros(n, 2 * ho, 2 * wo, cout, device=DEV, dtype=torch.bfloat16)
+            dyu[:, ::2, ::2] = dy
+            src = dyu
+        else:
+            src = dy
+        for _ in range(2):                                   # accumulates: two calls == 2x
+            _lib.call("bpb_conv_wgrad_bf16", x.data_ptr(), src.data_ptr(), dw.data_ptr(), n, h, w, cin, cout, k, s, up, S())
+        torch.cuda.synchronize()
+        err = relmax(dw, 2 * ref)
+        assert err < 2e-3, f"wgrad up={up} rel err {err}"
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 32, 32, 32, 3, 1), (4, 32, 16, 64, 128, 3, 1), (4, 64, 32, 256, 64, 3, 2),
+                                   (4, 64, 32, 64, 256, 1, 1), (8, 24, 8, 128, 256, 3, 2)])
+def test_conv_dgrad_is_forward_kernel_on_flipped_weights(shape):
+    """dX = conv(dY (zero-inserted for stride 2), W[ci][flipped taps][co], stride 1) and bpb_adam_pack(do_update=0)
+    produces exactly that operand layout."""
+    n, h, w, cin, cout, k, s = shape
+    g = torch.Generator().manual_seed(5)
+    pad = k // 2
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    wt = (torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5).to(DEV)
+    dy = torch.randn(n, ho, wo, cout, generator=g).to(torch.bfloat16).to(DEV)
+    # operand copies through the packing kernel
+    seg_dt = np.dtype([("off", "<i8"), ("numel", "<i8"), ("kind", "<i4"), ("trainable", "<i4"), ("cout", "<i4"),
+                       ("cin", "<i4"), ("k", "<i4"), ("pad", "<i4"), ("wf", "<u8"), ("wd", "<u8")])
+    assert seg_dt.itemsize == _lib.query("bpb_param_segment_bytes")
+    flat = wt.reshape(-1).clone()
+    wf = torch.zeros(cout, k * k * cin, device=DEV, dtype=torch.bfloat16)
+    wd = torch.zeros(cin, k * k * cout, device=DEV, dtype=torch.bfloat16)
+    seg = np.zeros(1, seg_dt)
+    seg[0] = (0, flat.numel(), 1, 1, cout, cin, k, 0, wf.data_ptr(), wd.data_ptr())
+    segd = torch.from_numpy(seg.view(np.uint8).copy()).to(DEV)
+    _lib.call("bpb_adam_pack", segd.data_ptr(), 1, flat.numel(), flat.data_ptr(), None, None, None, 0.0, 0.9, 0.999,
+              1e-8, 0.0, 1, 1.0, 0, S())
+    torch.cuda.synchronize()
+    assert torch.equal(wf, wt.permute(0, 2, 3, 1).reshape(cout, -1).to(torch.bfloat16))
+    assert torch.equal(wd, wt.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, -1).to(torch.bfloat16))
+    if s == 2:
+        src = torch.zeros(n, 2 * ho, 2 * wo, cout, device=DEV, dtype=torch.bfloat16)
+        src[:, ::2, ::2] = dy
+    else:
+        src = dy
+    dx = torch.empty(n, h, w, cin, device=DEV, dtype=torch.bfloat16)
+    _lib.call("bpb_conv_bf16", src.data_ptr(), wd.data_ptr(), dx.data_ptr(), None, n, src.shape[1], src.shape[2], cout, cin,
+              k, 1, 0, S())
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((n, cin, h, w), wt.to(torch.bfloat16).float(), dy.float().permute(0, 3, 1, 2),
+                                     stride=s, padding=pad).permute(0, 2, 3, 1)
+    assert relmax(dx.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("cfg", [(4, 32, 16, 64, 0, 0, 0), (4, 32, 16, 64, 0, 1, 0), (4, 16, 8, 128, 1, 0, 0),
+                                 (4, 8, 4, 256, 2, 0, 0), (4, 32, 16, 32, 0, 1, 1), (3, 16, 8, 512, 0, 0, 1)])
+def test_bn_backward_kernels(cfg):
+    """bpb_bn_bwd_reduce + bpb_bn_bwd_apply == autograd of train-mode BatchNorm (+ReLU gate, + nearest-upsample
+    adjoint, + zero-inserted output layout)."""
+    n, h, w, c, up, relu, zi = cfg
+    g = torch.Generator().manual_seed(11)
+    raw = (torch.randn(n, h, w, c, generator=g) * 1.5 + 0.3).to(torch.bfloat16).to(DEV)
+    f = 1 << up
+    dy = torch.randn(n, h * f, w * f, c, generator=g).to(torch.bfloat16).to(DEV)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(c, generator=g) * 0.2).to(DEV)
+    x = raw.float().reshape(-1, c)
+    mean, var = x.mean(0), x.var(0, unbiased=False)
+    istd = torch.rsqrt(var + 1e-5)
+    save = torch.stack([mean, istd]).contiguous()
+    scale = gamma * istd
+    shift = beta - mean * scale
+    # reference by autograd
+    xr = raw.float().clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.batch_norm(xr.permute(0, 3, 1, 2), None, None, gr, br, True, 0.0, 1e-5)
+    if relu:
+        y = F.relu(y)
+    if up:
+        y = F.interpolate(y, scale_factor=f, mode="nearest")
+    (y * dy.float().permute(0, 3, 1, 2)).sum().backward()
+    ws = torch.zeros(_lib.query("bpb_bn_bwd_workspace_bytes", c), dtype=torch.uint8, device=DEV)
+    coef = torch.empty(2, c, device=DEV)
+    dgam, dbet = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+    out = torch.full((n, h * (2 if zi else 1), w * (2 if zi else 1), c), float("nan"), device=DEV, dtype=torch.bfloat16)
+    for _ in range(2):                                       # workspace must come back clean
+        _lib.call("bpb_bn_bwd_reduce", dy.data_ptr(), raw.data_ptr(), save.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                  n, h, w, c, up, relu, 0, ws.data_ptr(), coef.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), S())
+    _lib.call("bpb_bn_bwd_apply", dy.data_ptr(), raw.data_ptr(), save.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+              coef.data_ptr(), n, h, w, c, up, relu, zi, out.data_ptr(), S())
+    torch.cuda.synchronize()
+    assert relmax(dgam, gr.grad) < 2e-3 and relmax(dbet, br.grad) < 2e-3
+    if zi:
+        o = out.float()
+        assert float(o[:, 1::2].abs().max()) == 0 and float(o[:, :, 1::2].abs().max()) == 0
+        got = o[:, ::2, ::2]
+    else:
+        got = out.float()
+    assert relmax(got, xr.grad) < 1e-2
+    assert int(ws.view(torch.int32).abs().sum()) == 0
+
+
+def test_relu_grad_sum_and_transpose():
+    g = torch.Generator().manual_seed(3)
+    m, c = 1000, 64
+    srcs = [torch.randn(m, c, generator=g).to(torch.bfloat16).to(DEV) for _ in range(3)]
+    y = torch.randn(m, c, generator=g).to(torch.bfloat16).to(DEV)
+    out = torch.empty_like(y)
+    import ctypes
+    arr = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in srcs])
+    _lib.call("bpb_relu_grad_sum", ctypes.cast(arr, ctypes.c_void_p), 3, y.data_ptr(), out.data_ptr(), m, c, S())
+    ref = (srcs[0].float() + srcs[1].float() + srcs[2].float()) * (y.float() > 0)
+    torch.cuda.synchronize()
+    assert relmax(out.float(), ref) < 8e-3
+    a = torch.randn(37, 53, generator=g).to(DEV)
+    t = torch.full((56, 40), float("nan"), device=DEV)
+    _lib.call("bpb_transpose_pad", a.data_ptr(), 53, 37, 53, t.data_ptr(), 40, 56, 40, S())
+    torch.cuda.synchronize()
+    assert torch.equal(t[:53, :37], a.t()) and float(t[53:].abs().sum()) == 0 and float(t[:, 37:].abs().sum()) == 0
+    # tf32 GEMM with a contraction length that is not a multiple of 32 (zero-filled tail)
+    A, W = torch.randn(50, 20, generator=g).to(DEV), torch.randn(70, 20, generator=g).to(DEV)
+    o = torch.empty(50, 72, device=DEV)
+    _lib.call("bpb_linear_tf32", A.data_ptr(), 20, W.data_ptr(), None, o.data_ptr(), 50, 70, 20, 72, 0, 0, S())
+    torch.cuda.synchronize()
+    assert relmax(o[:, :70], A @ W.t()) < 2e-3
+
+
+def test_adam_pack_matches_torch_adam():
+    g = torch.Generator().manual_seed(9)
+    co, ci, k = 32, 64, 3
+    p0, p1, p2 = torch.randn(100, generator=g), torch.randn(co, ci, k, k, generator=g) * 0.1, torch.randn(40, generator=g)
+    offs, tot = [0, 128, 128 + (p1.numel() + 63) // 64 * 64], 0
+    tot = offs[2] + 64
+    flat = torch.zeros(tot)
+    for o, p in zip(offs, (p0, p1, p2)):
+        flat[o:o + p.numel()] = p.reshape(-1)
+    flat = flat.to(DEV)
+    gr = torch.zeros(tot, device=DEV)
+    m_, v_ = torch.zeros(tot, device=DEV), torch.zeros(tot, device=DEV)
+    wf = torch.zeros(co, k * k * ci, device=DEV, dtype=torch.bfloat16)
+    wd = torch.zeros(ci, k * k * co, device=DEV, dtype=torch.bfloat16)
+    seg_dt = np.dtype([("off", "<i8"), ("numel", "<i8"), ("kind", "<i4"), ("trainable", "<i4"), ("cout", "<i4"),
+                       ("cin", "<i4"), ("k", "<i4"), ("pad", "<i4"), ("wf", "<u8"), ("wd", "<u8")])
+    seg = np.zeros(3, seg_dt)
+    seg[0] = (offs[0], 100, 0, 1, 0, 0, 0, 0, 0, 0)
+    seg[1] = (offs[1], p1.numel(), 1, 1, co, ci, k, 0, wf.data_ptr(), wd.data_ptr())
+    seg[2] = (offs[2], 40, 0, 0, 0, 0, 0, 0, 0, 0)          # frozen (e.g. BNClassifier bn.bias, bpbreid.py:407)
+    segd = torch.from_numpy(seg.view(np.uint8).copy()).to(DEV)
+    tp = [torch.nn.Parameter(t.clone().to(DEV)) for t in (p0, p1)]
+    opt = torch.optim.Adam(tp, lr=3.5e-4, weight_decay=5e-4)
+    for step in range(1, 4):
+        g0, g1 = torch.randn(100, generator=g).to(DEV), torch.randn(co, ci, k, k, generator=g).to(DEV)
+        gr[offs[0]:offs[0] + 100] = g0
+        gr[offs[1]:offs[1] + p1.numel()] = g1.permute(0, 2, 3, 1).reshape(-1)     # conv gradients arrive OHWI
+        _lib.call("bpb_adam_pack", segd.data_ptr(), 3, tot, flat.data_ptr(), gr.data_ptr(), m_.data_ptr(), v_.data_ptr(),
+                  3.5e-4, 0.9, 0.999, 1e-8, 5e-4, step, 1.0, 1, S())
+        tp[0].grad, tp[1].grad = g0, g1
+        opt.step()
+    torch.cuda.synchronize()
+    assert relmax(flat[offs[0]:offs[0] + 100], tp[0].data) < 1e-5
+    assert relmax(flat[offs[1]:offs[1] + p1.numel()].view_as(p1), tp[1].data) < 1e-5
+    assert torch.equal(flat[offs[2]:offs[2] + 40].cpu(), p2)
+    assert torch.equal(wf, tp[1].data.permute(0, 2, 3, 1).reshape(co, -1).to(torch.bfloat16)) or \
+        relmax(wf.float(), tp[1].data.permute(0, 2, 3, 1).reshape(co, -1)) < 1e-2
+
+
+def test_loss_backward_kernels():
+    from oracle import loss_oracle_torch as LT
+    g = torch.Generator().manual_seed(21)
+    n, c, ld = 24, 751, 768
+    logits = torch.randn(n, c, generator=g)
+    tg = torch.randint(0, c, (n,), generator=g)
+    lr = logits.clone().requires_grad_(True)
+    (2.5 * LT.cross_entropy_ls(lr, tg)).backward()
+    lg = torch.zeros(n, 752)
+    lg[:, :c] = logits
+    lg = lg.to(DEV)
+    dl = torch.zeros(n, ld, device=DEV)
+    _lib.call("bpb_ce_ls_bwd", lg.data_ptr(), 752, tg.to(DEV).data_ptr(), None, n, c, 0.1, 2.5, dl.data_ptr(), ld, S())
+    torch.cuda.synchronize()
+    assert relmax(dl[:, :c].cpu(), lr.grad) < 1e-4 and float(dl[:, c:].abs().sum()) == 0
+    # triplet: forward mining kernel + backward through the mined pairs; duplicates give no gradient
+    for margin in (0.3, 0.0):
+        n, K, D = 32, 5, 64
+        e = torch.randn(n, K, D, generator=g)
+        e[1] = e[0]
+        pid = (torch.arange(n) // 4)
+        er = e.clone().requires_grad_(True)
+        (1.7 * LT.part_averaged_triplet(er, pid, margin)).backward()
+        knd = e.permute(1, 0, 2).contiguous().to(DEV)
+        bufs = dict(dist=torch.empty(n, n, device=DEV), hp=torch.empty(n, device=DEV), hn=torch.empty(n, device=DEV),
+                    hpi=torch.empty(n, device=DEV, dtype=torch.int32), hni=torch.empty(n, device=DEV, dtype=torch.int32),
+                    out4=torch.empty(4, device=DEV))
+        _lib.call("bpb_triplet_fwd", knd.data_ptr(), pid.to(DEV).data_ptr(), None, 0, n, K, D, margin, bufs["dist"].data_ptr(),
+                  bufs["hp"].data_ptr(), bufs["hn"].data_ptr(), bufs["hpi"].data_ptr(), bufs["hni"].data_ptr(),
+                  bufs["out4"].data_ptr(), S())
+        de = torch.zeros(K, n, D, device=DEV)
+        _lib.call("bpb_triplet_bwd", knd.data_ptr(), None, 0, bufs["hp"].data_ptr(), bufs["hn"].data_ptr(),
+                  bufs["hpi"].data_ptr(), bufs["hni"].data_ptr(), bufs["out4"].data_ptr(), n, K, D, margin, 1.7,
+                  de.data_ptr(), S())
+        torch.cuda.synchronize()
+        assert relmax(de.permute(1, 0, 2).cpu(), er.grad) < 1e-3, margin
+    # BatchNorm1d backward with ReLU gate, strided operands, accumulation
+    m, c2 = 40, 96
+    x = torch.randn(m, c2, generator=g)
+    dy = torch.randn(m, 128, generator=g)
+    gam = torch.rand(c2, generator=g) + 0.5
+    xr, gr_ = x.clone().requires_grad_(True), gam.clone().requires_grad_(True)
+    y = F.relu(F.batch_norm(xr, None, None, gr_, torch.zeros(c2), True, 0.0, 1e-5))
+    (y * dy[:, :c2]).sum().backward()
+    dx = torch.ones(m, c2, device=DEV)
+    dg, db = torch.empty(c2, device=DEV), torch.empty(c2, device=DEV)
+    _lib.call("bpb_bn1d_bwd", dy.to(DEV).data_ptr(), 128, x.to(DEV).data_ptr(), c2, y.detach().to(DEV).data_ptr(), c2,
+              gam.to(DEV).data_ptr(), 1e-5, m, c2, dx.data_ptr(), c2, 1, dg.data_ptr(), db.data_ptr(), S())
+    torch.cuda.synchronize()
+    assert relmax(dx.cpu() - 1.0, xr.grad) < 1e-3 and relmax(dg.cpu(), gr_.grad) < 1e-3
+
+
+@pytest.fixture(scope="module")
+def trained():
+    """One fused training step of the contractive HRNet case with per-layer backward records kept."""
+    c = GI.model_case("hrnet32_k5_ctr")
+    m = c["model"]
+    m.load_state_dict(c["state_dict"])
+    m = m.to(DEV)
+    m.materialize_spatial_features = False
+    crit = losses.GiLtLoss(None, use_visibility_scores=False, triplet_margin=0.3, use_gpu=True)
+    ts = train.TrainStep(m, crit, None, bpa_weight=0.35, use_graph=False)
+    ts.debug = True
+    plan = ts.forward_backward(torch.from_numpy(c["images"]).to(DEV), torch.from_numpy(c["pids"]).to(DEV),
+                               torch.from_numpy(c["masks"]).to(DEV))
+    torch.cuda.synchronize()
+    return c, m, ts, plan
+
+
+def test_train_loss_matches_reference(trained, golden):
+    c, m, ts, plan = trained
+    g = golden("grads_hrnet32_k5_ctr")
+    loss = float(plan.loss_out[0])
+    print("train-mode loss", loss, "reference", float(g["loss"]))
+    assert abs(loss - float(g["loss"])) < 1e-2 * abs(float(g["loss"]))
+
+
+def test_every_conv_bn_backward_teacher_forced(trained):
+    """Each of the ~320 conv+BN pairs of the real network: BatchNorm backward, tensor-core wgrad and dgrad checked
+    against fp32 PyTorch on the layer's ACTUAL operands (the activations / incoming gradients of the CUDA run)."""
+    c, m, ts, plan = trained
+    fl = ts.flat
+    worst = dict(draw=(0, ""), dw=(0, ""), dx=(0, ""), dgamma=(0, ""))
+    assert len(plan.btrace) > 300
+    for rec in plan.btrace:
+        lz, dy, up = rec["lz"], rec["dy"], rec["up"]
+        raw, conv, bn = lz.raw, lz.conv, lz.bn
+        x = raw.t.float()
+        cch = raw.c
+        g_ = dy.t.float()
+        if up:
+            f = 1 << up
+            g_ = g_.view(raw.n, raw.h, f, raw.w, f, cch).sum(dim=(2, 4))
+        if rec["relu_affine"]:
+            g_ = g_ * ((x * lz.scale + lz.shift) > 0)
+        mean, istd = lz.save[0], lz.save[1]
+        xh = (x - mean) * istd
+        M = x.numel() // cch
+        sg, sgx = g_.reshape(-1, cch).sum(0), (g_ * xh).reshape(-1, cch).sum(0)
+        draw_ref = lz.scale * (g_ - sg / M - xh * (sgx / M))
+        draw = rec["draw"].t.float()
+        if rec["zero_ins"]:
+            draw = draw[:, ::2, ::2]
+        e = relmax(draw, draw_ref)
+        if e > worst["draw"][0]:
+            worst["draw"] = (e, rec["name"])
+        e = relmax(fl.grad_view(bn.weight), sgx)
+        if e > worst["dgamma"][0]:
+            worst["dgamma"] = (e, rec["name"])
+        if lz.kind == "stem":
+            img = plan.images.to(torch.bfloat16).float()
+            ref = torch.nn.grad.conv2d_weight(img, conv.weight.shape, draw.permute(0, 3, 1, 2), stride=2, padding=1)
+            e = relmax(fl.grad_view(conv.weight), ref)
+        else:
+            xin = lz.x_in.t.float().permute(0, 3, 1, 2)
+            k, s = conv.kernel_size[0], conv.stride[0]
+            ref = torch.nn.grad.conv2d_weight(xin, conv.weight.shape, draw.permute(0, 3, 1, 2), stride=s, padding=k // 2)
+            e = relmax(fl.conv_grad_view(conv), ref)
+            wq = conv.weight.detach().to(torch.bfloat16).float()
+            dref = torch.nn.grad.conv2d_input(xin.shape, wq, draw.permute(0, 3, 1, 2), stride=s, padding=k // 2)
+            ex = relmax(rec["dx"].t.float().permute(0, 3, 1, 2), dref)
+            if ex > worst["dx"][0]:
+                worst["dx"] = (ex, rec["name"])
+        if e > worst["dw"][0]:
+            worst["dw"] = (e, rec["name"])
+    print("teacher-forced backward, worst relative errors:", worst)
+    assert worst["draw"][0] < 1.5e-2 and worst["dx"][0] < 1.5e-2, worst
+    assert worst["dw"][0] < 5e-3 and worst["dgamma"][0] < 5e-3, worst
+
+
+def test_end_to_end_gradients_vs_oracle_autograd(trained):
+    """Every parameter gradient of the fused step vs torch autograd over the fp32 oracle (the contractive weights keep
+    the bf16 forward within ~1e-2 of fp32, so the end-to-end comparison is meaningful)."""
+    from tests.test_oracle_vs_golden import oracle_grads
+    c, m, ts, plan = trained
+    loss, og = oracle_grads(c)
+    got = ts.grads()
+    rows = []
+    for k, gt in got.items():
+        ref = og[k].to(DEV)
+        if float(ref.norm()) < 1e-4:
+            continue
+        rows.append((rel(gt, ref), k))
+    rows.sort(reverse=True)
+    print("end-to-end gradient error (|d|/|ref|), worst 12:", rows[:12])
+    med = float(np.median([r[0] for r in rows]))
+    print("median", med, "count", len(rows))
+    assert len(rows) > 900
+    assert med < 3e-2 and rows[0][0] < 0.25, (med, rows[:5])
+
+
+def test_optimizer_step_moves_parameters_like_adam(trained):
+    c, m, ts, plan = trained
+    fl = ts.flat
+    before = fl.p.clone()
+    grads = fl.g.clone()
+    ts._optimizer(plan)
+    torch.cuda.synchronize()
+    delta = fl.p - before
+    # first Adam step: |delta| = lr * |g_hat| / (|g_hat| + eps) ~= lr for every element with a gradient
+    wname = "global_identity_classifier.classifier.weight"
+    p = dict(m.named_parameters())[wname]
+    o = fl.off[id(p)]
+    d = delta[o:o + p.numel()]
+    gsel = grads[o:o + p.numel()] + 5e-4 * before[o:o + p.numel()]
+    assert torch.allclose(d, -3.5e-4 * torch.sign(gsel) * (gsel.abs() / (gsel.abs() + 1e-8)), atol=1e-6)
+    frozen = dict(m.named_parameters())["global_identity_classifier.bn.bias"]
+    of = fl.off[id(frozen)]
+    assert float(delta[of:of + frozen.numel()].abs().max()) == 0
