@@ -47,6 +47,9 @@ _SIGS = {
     "bpb_vis_unpack": [_P, _P, _I, _I, _P, _P, _P],
     "bpb_weighted_sum": [_P, _P, _I, _P, _P],
     "bpb_triplet_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P],
+    "bpb_triplet_fwd_rows": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "bpb_triplet_finish": [_P, _P, _P],
+    "bpb_triplet_bwd_rows": [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P],
     "bpb_ce_ls_fwd": [_P, _L, _P, _P, _I, _I, _F, _I, _P, _P, _P],
     "bpb_pixel_ce_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     "bpb_part_distance": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],

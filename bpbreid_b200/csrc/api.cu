@@ -205,6 +205,13 @@ int bpb_triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis
     return triplet_fwd(emb_knd, labels, vis, vis_mode, n, k, d, margin, dist_nn, hp, hn, hp_idx, hn_idx, out4,
                        S(stream));
 }
+int bpb_triplet_fwd_rows(const float* emb, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
+                         float margin, int row_lo, int rows, int n_local, int sums_mode, float* dist_rows, float* hp,
+                         float* hn, int* hp_idx, int* hn_idx, float* out4, void* stream) {
+    return triplet_fwd_rows(emb, labels, vis, vis_mode, n, k, d, margin, row_lo, rows, n_local, sums_mode, dist_rows, hp,
+                            hn, hp_idx, hn_idx, out4, S(stream));
+}
+int bpb_triplet_finish(const float* sums4, float* out4, void* stream) { return triplet_finish(sums4, out4, S(stream)); }
 int bpb_ce_ls_fwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c,
                   float eps, int acc_mode, float* scratch, float* out2, void* stream) {
     return ce_ls_fwd(logits, ld, targets, weights, n, c, eps, acc_mode, scratch, out2, S(stream));
@@ -283,6 +290,12 @@ int bpb_triplet_bwd(const float* emb_knd, const void* vis, int vis_mode, const f
                     float loss_weight, float* demb_knd, void* stream) {
     return triplet_bwd(emb_knd, vis, vis_mode, hp, hn, hp_idx, hn_idx, out4, n, k, d, margin, loss_weight, demb_knd,
                        S(stream));
+}
+int bpb_triplet_bwd_rows(const float* emb, const void* vis, int vis_mode, const float* hp, const float* hn,
+                         const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
+                         float loss_weight, int row_lo, int rows, int n_local, float* demb, void* stream) {
+    return triplet_bwd_rows(emb, vis, vis_mode, hp, hn, hp_idx, hn_idx, out4, n, k, d, margin, loss_weight, row_lo, rows,
+                            n_local, demb, S(stream));
 }
 int bpb_bn1d_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* y, int64_t ld_y,
                  const float* gamma, float eps, int m, int c, float* dx, int64_t ld_dx, int accumulate, float* dgamma,

@@ -79,6 +79,10 @@ int head_branch_pool(const void* x, const float* mt, const float* mask_sum, int 
 int triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
                 float margin, float* dist_nn, float* hp, float* hn, int* hp_idx, int* hn_idx, float* out4,
                 cudaStream_t stream);
+int triplet_fwd_rows(const float* emb, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
+                     float margin, int row_lo, int rows, int n_local, int sums_mode, float* dist_rows, float* hp,
+                     float* hn, int* hp_idx, int* hn_idx, float* out4, cudaStream_t stream);
+int triplet_finish(const float* sums4, float* out4, cudaStream_t stream);
 int ce_ls_fwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c, float eps,
               int acc_mode, float* row_loss, float* out2, cudaStream_t stream);
 int pixel_ce_fwd(const float* logits_nchw, const float* target_masks, int n, int kp1, int hf, int wf, int hm, int wm,
@@ -133,6 +137,9 @@ int ce_ls_bwd(const float* logits, int64_t ld, const int64_t* targets, const flo
 int triplet_bwd(const float* emb_knd, const void* vis, int vis_mode, const float* hp, const float* hn,
                 const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
                 float loss_weight, float* demb_knd, cudaStream_t stream);
+int triplet_bwd_rows(const float* emb, const void* vis, int vis_mode, const float* hp, const float* hn,
+                     const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
+                     float loss_weight, int row_lo, int rows, int n_local, float* demb, cudaStream_t stream);
 int bn1d_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* y, int64_t ld_y,
              const float* gamma, float eps, int m, int c, float* dx, int64_t ld_dx, int accumulate, float* dgamma,
              float* dbeta, cudaStream_t stream);

@@ -19,23 +19,33 @@ constexpr int kDC = 64;        // feature chunk
 
 // dot(a,b) accumulated d = 0..D-1 with one fp32 FMA chain: the diagonal (a == b) and duplicated embeddings give
 // bit-identical values for |a|^2 and <a,b>, so d^2 is exactly 0 where the reference's is (":88-91" zero mask).
+// Embedding layout: [shards][K][n_local][D] (shards * n_local == n; one shard = the plain [K, N, D] tensor).  With several
+// GPUs every rank contributes one shard through a single all-gather and computes only ITS anchor rows
+// [row_lo, row_lo + rows) of the pairwise matrix -- the reference gathers the whole batch on GPU 0
+// (part_based_engine.py:82-95) and mines there; the mined pairs are identical.
+__device__ __forceinline__ const float* emb_row(const float* emb, int k, int j, int kparts, int n_local, int d) {
+    const int sh = j / n_local, jl = j - sh * n_local;
+    return emb + ((static_cast<int64_t>(sh) * kparts + k) * n_local + jl) * d;
+}
+
 __global__ void __launch_bounds__(256) pair_dist_kernel(const float* __restrict__ emb, const void* __restrict__ vis,
-                                                        int vis_mode, int n, int kparts, int d,
-                                                        float* __restrict__ dist) {
+                                                        int vis_mode, int n, int kparts, int d, int row_lo, int rows,
+                                                        int n_local, float* __restrict__ dist) {
     __shared__ float sa[kPT][kDC + 1], sb[kPT][kDC + 1];
     __shared__ float sqa[kPT], sqb[kPT];
     const int ti = threadIdx.x / kPT, tj = threadIdx.x % kPT;
-    const int i = blockIdx.y * kPT + ti, j = blockIdx.x * kPT + tj;
+    const int il = blockIdx.y * kPT + ti;                      // local anchor row
+    const int i = row_lo + il, j = blockIdx.x * kPT + tj;
     float num = 0.f, den = 0.f;
     for (int k = 0; k < kparts; ++k) {
-        const float* e = emb + static_cast<int64_t>(k) * n * d;
         float dot = 0.f, qa = 0.f, qb = 0.f;   // qa/qb: only threads with tj==0 / ti==0 use them
         for (int d0 = 0; d0 < d; d0 += kDC) {
             for (int t = threadIdx.x; t < kPT * kDC; t += 256) {
                 const int r = t / kDC, cc = t % kDC;
-                const int ra = blockIdx.y * kPT + r, rb = blockIdx.x * kPT + r;
-                sa[r][cc] = (ra < n && d0 + cc < d) ? e[static_cast<int64_t>(ra) * d + d0 + cc] : 0.f;
-                sb[r][cc] = (rb < n && d0 + cc < d) ? e[static_cast<int64_t>(rb) * d + d0 + cc] : 0.f;
+                const int ral = blockIdx.y * kPT + r, rb = blockIdx.x * kPT + r;
+                const int ra = row_lo + ral;
+                sa[r][cc] = (ral < rows && d0 + cc < d) ? emb_row(emb, k, ra, kparts, n_local, d)[d0 + cc] : 0.f;
+                sb[r][cc] = (rb < n && d0 + cc < d) ? emb_row(emb, k, rb, kparts, n_local, d)[d0 + cc] : 0.f;
             }
             __syncthreads();
 #pragma unroll 8
@@ -56,10 +66,10 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const float* __restrict_
         const float zero = d2 == 0.f ? 1.f : 0.f;
         float dd = sqrtf(d2 + zero * 1e-16f) * (1.f - zero);
         float w = 1.f;
-        if (vis_mode == 1 && i < n && j < n) {
+        if (vis_mode == 1 && il < rows && j < n) {
             const uint8_t* v = reinterpret_cast<const uint8_t*>(vis);
             w = (v[static_cast<int64_t>(i) * kparts + k] && v[static_cast<int64_t>(j) * kparts + k]) ? 1.f : 0.f;
-        } else if (vis_mode == 2 && i < n && j < n) {
+        } else if (vis_mode == 2 && il < rows && j < n) {
             const float* v = reinterpret_cast<const float*>(vis);
             w = sqrtf(v[static_cast<int64_t>(i) * kparts + k] * v[static_cast<int64_t>(j) * kparts + k]);
         }
@@ -67,26 +77,28 @@ __global__ void __launch_bounds__(256) pair_dist_kernel(const float* __restrict_
         den += w;
         __syncthreads();
     }
-    if (i < n && j < n) {
+    if (il < rows && j < n) {
         float out;
         if (vis_mode == 0) out = num / static_cast<float>(kparts);          // pd.mean(0)
         else out = den == 0.f ? -1.f : num / den;                            // masked_mean with the -1 sentinel
-        dist[static_cast<int64_t>(i) * n + j] = out;
+        dist[static_cast<int64_t>(il) * n + j] = out;
     }
 }
 
 // one warp per anchor: hardest positive (max) / hardest negative (min) with first-occurrence indices
 __global__ void __launch_bounds__(256) mine_kernel(const float* __restrict__ dist, const int64_t* __restrict__ labels,
-                                                   int n, float* __restrict__ hp, float* __restrict__ hn,
-                                                   int* __restrict__ hp_idx, int* __restrict__ hn_idx) {
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                                                   int n, int row_lo, int rows, float* __restrict__ hp,
+                                                   float* __restrict__ hn, int* __restrict__ hp_idx,
+                                                   int* __restrict__ hn_idx) {
+    const int il = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (i >= n) return;
+    if (il >= rows) return;
+    const int i = row_lo + il;
     const int64_t li = labels[i];
     float bp = -1.f, bn = FLT_MAX;
     int ip = 0x7fffffff, in_ = 0x7fffffff;
     for (int j = lane; j < n; j += 32) {
-        const float dv = dist[static_cast<int64_t>(i) * n + j];
+        const float dv = dist[static_cast<int64_t>(il) * n + j];
         const bool valid = dv != -1.f;
         const bool same = labels[j] == li;
         // reference: d*mask - (~mask)  and  d*mask + (~mask)*FLT_MAX
@@ -105,15 +117,16 @@ __global__ void __launch_bounds__(256) mine_kernel(const float* __restrict__ dis
         if (obn < bn || (obn == bn && oin < in_)) { bn = obn; in_ = oin; }
     }
     if (lane == 0) {
-        hp[i] = bp; hn[i] = bn;
-        hp_idx[i] = bp == -1.f ? -1 : ip;
-        hn_idx[i] = bn == FLT_MAX ? -1 : in_;
+        hp[il] = bp; hn[il] = bn;
+        hp_idx[il] = bp == -1.f ? -1 : ip;
+        hn_idx[il] = bn == FLT_MAX ? -1 : in_;
     }
 }
 
-// out4 = [loss, trivial_ratio, valid_ratio, n_valid]
+// out4 = [loss, trivial_ratio, valid_ratio, n_valid]; sums_mode: [sum loss, sum trivial, n_valid, rows] (partial sums
+// of one rank's anchor rows, all-reduced across ranks and turned into the ratios by triplet_finish_kernel)
 __global__ void __launch_bounds__(256) triplet_finalize_kernel(const float* hp, const float* hn, int n, float margin,
-                                                               float* out4) {
+                                                               int sums_mode, float* out4) {
     __shared__ float rl[256], rt[256], rv[256];
     float l = 0.f, t = 0.f, v = 0.f;
     const bool soft = margin <= 0.f;
@@ -138,25 +151,55 @@ __global__ void __launch_bounds__(256) triplet_finalize_kernel(const float* hp, 
     }
     if (threadIdx.x == 0) {
         const float nv = rv[0];
-        out4[0] = nv > 0.f ? rl[0] / nv : nanf("");
-        out4[1] = nv > 0.f ? rt[0] / nv : 0.f;
-        out4[2] = nv / static_cast<float>(n);
+        if (sums_mode) {
+            out4[0] = rl[0]; out4[1] = rt[0]; out4[2] = nv; out4[3] = static_cast<float>(n);
+        } else {
+            out4[0] = nv > 0.f ? rl[0] / nv : nanf("");
+            out4[1] = nv > 0.f ? rt[0] / nv : 0.f;
+            out4[2] = nv / static_cast<float>(n);
+            out4[3] = nv;
+        }
+    }
+}
+
+__global__ void triplet_finish_kernel(const float* sums4, float* out4) {
+    if (threadIdx.x == 0) {
+        const float sl = sums4[0], st = sums4[1], nv = sums4[2], rows = sums4[3];
+        out4[0] = nv > 0.f ? sl / nv : nanf("");
+        out4[1] = nv > 0.f ? st / nv : 0.f;
+        out4[2] = rows > 0.f ? nv / rows : 0.f;
         out4[3] = nv;
     }
+}
+
+int triplet_fwd_rows(const float* emb, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
+                     float margin, int row_lo, int rows, int n_local, int sums_mode, float* dist_rows, float* hp,
+                     float* hn, int* hp_idx, int* hn_idx, float* out4, cudaStream_t stream) {
+    BPB_CHECK(vis_mode >= 0 && vis_mode <= 2, "triplet_fwd: vis_mode %d", vis_mode);
+    BPB_CHECK(vis_mode == 0 || vis != nullptr, "triplet_fwd: visibility pointer missing");
+    BPB_CHECK(n_local >= 1 && n % n_local == 0, "triplet_fwd: n=%d is not a multiple of the shard size %d", n, n_local);
+    BPB_CHECK(row_lo >= 0 && rows >= 1 && row_lo + rows <= n, "triplet_fwd: anchor rows [%d,+%d) outside [0,%d)", row_lo,
+              rows, n);
+    dim3 grid(ceil_div(n, kPT), ceil_div(rows, kPT));
+    pair_dist_kernel<<<grid, 256, 0, stream>>>(emb, vis, vis_mode, n, k, d, row_lo, rows, n_local, dist_rows);
+    BPB_LAUNCH_CHECK("pair_dist_kernel");
+    mine_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(dist_rows, labels, n, row_lo, rows, hp, hn, hp_idx, hn_idx);
+    BPB_LAUNCH_CHECK("mine_kernel");
+    triplet_finalize_kernel<<<1, 256, 0, stream>>>(hp, hn, rows, margin, sums_mode, out4);
+    BPB_LAUNCH_CHECK("triplet_finalize_kernel");
+    return 0;
 }
 
 int triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
                 float margin, float* dist_nn, float* hp, float* hn, int* hp_idx, int* hn_idx, float* out4,
                 cudaStream_t stream) {
-    BPB_CHECK(vis_mode >= 0 && vis_mode <= 2, "triplet_fwd: vis_mode %d", vis_mode);
-    BPB_CHECK(vis_mode == 0 || vis != nullptr, "triplet_fwd: visibility pointer missing");
-    dim3 grid(ceil_div(n, kPT), ceil_div(n, kPT));
-    pair_dist_kernel<<<grid, 256, 0, stream>>>(emb_knd, vis, vis_mode, n, k, d, dist_nn);
-    BPB_LAUNCH_CHECK("pair_dist_kernel");
-    mine_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(dist_nn, labels, n, hp, hn, hp_idx, hn_idx);
-    BPB_LAUNCH_CHECK("mine_kernel");
-    triplet_finalize_kernel<<<1, 256, 0, stream>>>(hp, hn, n, margin, out4);
-    BPB_LAUNCH_CHECK("triplet_finalize_kernel");
+    return triplet_fwd_rows(emb_knd, labels, vis, vis_mode, n, k, d, margin, 0, n, n, 0, dist_nn, hp, hn, hp_idx, hn_idx,
+                            out4, stream);
+}
+
+int triplet_finish(const float* sums4, float* out4, cudaStream_t stream) {
+    triplet_finish_kernel<<<1, 32, 0, stream>>>(sums4, out4);
+    BPB_LAUNCH_CHECK("triplet_finish_kernel");
     return 0;
 }
 

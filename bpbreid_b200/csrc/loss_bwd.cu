@@ -76,9 +76,11 @@ __global__ void __launch_bounds__(128) triplet_bwd_kernel(const float* __restric
                                                           const float* __restrict__ hn, const int* __restrict__ hp_idx,
                                                           const int* __restrict__ hn_idx,
                                                           const float* __restrict__ out4, int n, int kparts, int d,
-                                                          float margin, float loss_weight, float* __restrict__ demb) {
-    const int i = blockIdx.x;
-    const float hpv = hp[i], hnv = hn[i];
+                                                          float margin, float loss_weight, int row_lo, int n_local,
+                                                          float* __restrict__ demb) {
+    const int il = blockIdx.x;                             // local anchor row; hp / hn / indices are per local row
+    const int i = row_lo + il;
+    const float hpv = hp[il], hnv = hn[il];
     if (hpv == -1.f || hnv == FLT_MAX) return;
     const float nvalid = out4[3];
     if (!(nvalid > 0.f)) return;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(128) triplet_bwd_kernel(const float* __restric
     __shared__ float red[4];
     __shared__ float s_d;
     for (int pair = 0; pair < 2; ++pair) {
-        const int j = pair == 0 ? hp_idx[i] : hn_idx[i];
+        const int j = pair == 0 ? hp_idx[il] : hn_idx[il];
         const float sign = pair == 0 ? a : -a;
         if (j < 0) continue;
         // weights of the masked mean (tensortools.py:10-19) for this pair
@@ -124,8 +126,11 @@ __global__ void __launch_bounds__(128) triplet_bwd_kernel(const float* __restric
                 w = sqrtf(v[static_cast<int64_t>(i) * kparts + k] * v[static_cast<int64_t>(j) * kparts + k]);
             }
             if (w == 0.f) continue;                        // block-uniform
-            const float* ei = emb + (static_cast<int64_t>(k) * n + i) * d;
-            const float* ej = emb + (static_cast<int64_t>(k) * n + j) * d;
+            // [shards][K][n_local][D] layout (see pair_dist_kernel); one shard == the plain [K, N, D] tensor
+            const int64_t oi = ((static_cast<int64_t>(i / n_local) * kparts + k) * n_local + i % n_local) * d;
+            const int64_t oj = ((static_cast<int64_t>(j / n_local) * kparts + k) * n_local + j % n_local) * d;
+            const float* ei = emb + oi;
+            const float* ej = emb + oj;
             float q = 0.f;
             for (int t = threadIdx.x; t < d; t += 128) {
                 const float df = ei[t] - ej[t];
@@ -140,8 +145,8 @@ __global__ void __launch_bounds__(128) triplet_bwd_kernel(const float* __restric
             const float dk = s_d;
             if (dk == 0.f) continue;                       // exact-zero mask: no gradient
             const float cf = sign * w / (den * dk);
-            float* gi = demb + (static_cast<int64_t>(k) * n + i) * d;
-            float* gj = demb + (static_cast<int64_t>(k) * n + j) * d;
+            float* gi = demb + oi;
+            float* gj = demb + oj;
             for (int t = threadIdx.x; t < d; t += 128) {
                 const float g = cf * (ei[t] - ej[t]);
                 atomicAdd(gi + t, g);
@@ -151,14 +156,23 @@ __global__ void __launch_bounds__(128) triplet_bwd_kernel(const float* __restric
     }
 }
 
+int triplet_bwd_rows(const float* emb, const void* vis, int vis_mode, const float* hp, const float* hn,
+                     const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
+                     float loss_weight, int row_lo, int rows, int n_local, float* demb, cudaStream_t stream) {
+    BPB_CHECK(vis_mode >= 0 && vis_mode <= 2, "triplet_bwd: vis_mode %d", vis_mode);
+    BPB_CHECK(n_local >= 1 && n % n_local == 0 && row_lo >= 0 && rows >= 1 && row_lo + rows <= n,
+              "triplet_bwd: bad row range / shard size");
+    triplet_bwd_kernel<<<rows, 128, 0, stream>>>(emb, vis, vis_mode, hp, hn, hp_idx, hn_idx, out4, n, k, d, margin,
+                                                 loss_weight, row_lo, n_local, demb);
+    BPB_LAUNCH_CHECK("triplet_bwd_kernel");
+    return 0;
+}
+
 int triplet_bwd(const float* emb_knd, const void* vis, int vis_mode, const float* hp, const float* hn,
                 const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
                 float loss_weight, float* demb_knd, cudaStream_t stream) {
-    BPB_CHECK(vis_mode >= 0 && vis_mode <= 2, "triplet_bwd: vis_mode %d", vis_mode);
-    triplet_bwd_kernel<<<n, 128, 0, stream>>>(emb_knd, vis, vis_mode, hp, hn, hp_idx, hn_idx, out4, n, k, d, margin,
-                                              loss_weight, demb_knd);
-    BPB_LAUNCH_CHECK("triplet_bwd_kernel");
-    return 0;
+    return triplet_bwd_rows(emb_knd, vis, vis_mode, hp, hn, hp_idx, hn_idx, out4, n, k, d, margin, loss_weight, 0, n, n,
+                            demb_knd, stream);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -423,14 +423,17 @@ class ForwardPlan:
                 x = self.bottleneck(x, blk)
             t = bb.transition1
             xs = [self.conv_bn_relu(x, t[0][0], t[0][1]), self.conv_bn_relu(x, t[1][0][0], t[1][0][1])]
+            self.mark("stage2")
             for mod in bb.stage2:
                 xs = self.hr_module(xs, mod)
             t = bb.transition2[2][0]
             xs = xs + [self.conv_bn_relu(xs[-1], t[0], t[1])]
+            self.mark("stage3")
             for mod in bb.stage3:
                 xs = self.hr_module(xs, mod)
             t = bb.transition3[3][0]
             xs = xs + [self.conv_bn_relu(xs[-1], t[0], t[1])]
+            self.mark("stage4")
             for mod in bb.stage4:
                 xs = self.hr_module(xs, mod)
             br = []
@@ -441,6 +444,10 @@ class ForwardPlan:
             self.join()
             keep.extend(br)
         return br
+
+    def mark(self, name):
+        """position marker (gradient mode: the backward of everything recorded AFTER this point is complete when the
+        reversed tape reaches it -> a gradient bucket can be all-reduced while the earlier layers' backward runs)"""
 
     def hrnet_concat(self, br) -> Act:
         """bilinear(align_corners) upsample + concat (hrnet.py:568-573): only needed when the caller wants the

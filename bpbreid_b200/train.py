@@ -142,13 +142,21 @@ class TrainPlan(ForwardPlan):
         self._gl = {}                  # data_ptr of an activation -> list of gradient Acts
         self._gfree = {}
         self._gref = {}
+        self._gall = []
         self.bwd_ws = {}
         self.btrace = []               # debug: one record per conv+BN backward (teacher-forced kernel checks in tests)
+        self.head_dx = []              # debug: gradients w.r.t. the branch maps as the head backward leaves them
+        self.marks = []                # (index into bops, stage name): gradient-bucket boundaries for the all-reduce
         super().__init__(model, n, h, w, True, device, "tc", False, debug, grad=True, flat=flat)
 
     # ------------------------------------------------------------------ gradient bookkeeping
+    # Gradient buffers are plain device tensors whose raw pointers are baked into the recorded launches, so the plan
+    # must own them for its whole life (self._gall); a buffer goes back to the free list -- and may be handed out
+    # again -- only once every launch that reads it has been RECORDED (launches replay in recording order on one
+    # stream, so a later writer can never overtake an earlier reader).
     def g_add(self, act: Act, g: Act):
         self._gl.setdefault(act.t.data_ptr(), []).append(g)
+        self._gref[id(g.buf)] += 1
 
     def g_take(self, act: Act):
         return self._gl.pop(act.t.data_ptr(), [])
@@ -156,8 +164,24 @@ class TrainPlan(ForwardPlan):
     def galloc(self, n, h, w, c) -> Act:
         nbytes = n * h * w * c * 2
         lst = self._gfree.get(nbytes)
-        buf = lst.pop() if lst else torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if lst:
+            buf = lst.pop()
+        else:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._gall.append(buf)
+        self._gref[id(buf)] = 0
         return Act(buf.view(torch.bfloat16).view(n, h, w, c), n, h, w, c, buf)
+
+    def g_release(self, g: Act):
+        """one consumer of `g` has been recorded"""
+        self._gref[id(g.buf)] -= 1
+        self.g_done(g)
+
+    def g_done(self, g: Act):
+        """return `g` to the pool if nobody else is going to read it (never in debug mode: tests inspect the buffers)"""
+        if self._gref[id(g.buf)] <= 0 and not self.debug:
+            self._gref[id(g.buf)] = 1 << 30                    # guards against a double free
+            self._gfree.setdefault(g.buf.numel(), []).append(g.buf)
 
     def _bop(self, name, *args):
         self.bops.append((getattr(self.lib, name), args, name))
@@ -172,14 +196,18 @@ class TrainPlan(ForwardPlan):
     def grad_sum(self, grads, y: Act | None):
         """g = (sum grads) * [y > 0]"""
         like = grads[0]
+        partials = []
         while len(grads) > 4:                                   # (never happens on the shipped topologies)
             part = self.galloc(like.n, like.h, like.w, like.c)
             self._bop("bpb_relu_grad_sum", self._ptr_array([g.t for g in grads[:4]]), 4, None, part.t.data_ptr(),
                       like.m, like.c)
-            grads = [part] + grads[4:]
+            grads = [part] + list(grads[4:])
+            partials.append(part)
         out = self.galloc(like.n, like.h, like.w, like.c)
         self._bop("bpb_relu_grad_sum", self._ptr_array([g.t for g in grads]), len(grads),
                   None if y is None else y.t.data_ptr(), out.t.data_ptr(), like.m, like.c)
+        for part in partials:
+            self.g_done(part)
         return out
 
     # ------------------------------------------------------------------ backward of the conv + BN pair
@@ -204,6 +232,7 @@ class TrainPlan(ForwardPlan):
         if lz.kind == "stem":
             self._bop("bpb_stem_wgrad", self.images.data_ptr(), draw.t.data_ptr(), fl.grad_ptr(conv.weight), self.n,
                       self.h, self.w, conv.out_channels, k, stride)
+            self.g_done(draw)
             return
         x = lz.x_in
         cin, cout = conv.in_channels, conv.out_channels
@@ -219,6 +248,7 @@ class TrainPlan(ForwardPlan):
         if self.debug:
             self.btrace[-1]["dx"] = dx
         self.g_add(x, dx)
+        self.g_done(draw)
 
     # ------------------------------------------------------------------ taped building blocks
     def apply(self, lz: Lazy, relu, res=None) -> Act:
@@ -239,6 +269,11 @@ class TrainPlan(ForwardPlan):
                     self.lazy_backward(res, dy, 0, 0)
                 else:
                     self.g_add(res, dy)
+            fresh = all(dy is not g for g in grads)
+            for g in grads:
+                self.g_release(g)
+            if fresh:
+                self.g_done(dy)
         self.tape.append(bwd)
         return y
 
@@ -256,8 +291,14 @@ class TrainPlan(ForwardPlan):
                 else:
                     assert up == 0
                     self.g_add(t, g)
+            for gg in grads:
+                self.g_release(gg)
+            self.g_done(g)
         self.tape.append(bwd)
         return y
+
+    def mark(self, name):
+        self.tape.append(lambda: self.marks.append((len(self.bops), name)))
 
     def ibn_relu(self, x, conv, ibn):
         raise NotImplementedError("training backward of the IBN backbone is not built (SURVEY.md section 8 config 4)")
@@ -310,6 +351,10 @@ class TrainPlan(ForwardPlan):
                           hf["wf"].data_ptr(), coefab.data_ptr(), n, b.h, b.w, b.c, off, ctot, h, w, kp1,
                           dx.t.data_ptr())
                 self.g_add(b, dx)
+                if self.debug:
+                    self.head_dx.append(dx)
+            if self.debug:
+                self.head_dbg = dict(dms=dms, dmts=dmts, dlows=dlows, dwf=dwf, dbf=dbf, coefab=coefab)
         self.tape.append(bwd)
         return ctot
 
@@ -501,9 +546,19 @@ class TrainStep:
         plan.tri = []
         tri_keys = [(PARTS, plan.emb[3 * n:], plan.d_emb[3 * n:], K), (FOREGROUND, plan.emb[n:], plan.d_emb[n:], 1),
                     (GLOBAL, plan.emb[0:], plan.d_emb[0:], 1)]
+        plan.sharded = []                                        # (ShardedTriplet, local emb view, local grad view, weight)
         for key, e, de, kk in tri_keys:
             wgt = float(lw[key]["tr"])
             if wgt <= 0:
+                continue
+            if world > 1:
+                # global-batch mining with per-rank anchor rows (bpbreid_b200.distributed.ShardedTriplet): the NCCL calls
+                # sit between recorded launch segments, see _launch
+                from .distributed import ShardedTriplet
+                st = ShardedTriplet(n, kk, D, margin, dev, self.group)
+                plan.sharded.append((st, e[:kk * n].view(kk, n, D), de[:kk * n].view(kk, n, D), wgt))
+                terms.append(st.out4)
+                weights.append(wgt)
                 continue
             bufs = dict(dist=torch.empty(n, n, device=dev), hp=torch.empty(n, device=dev), hn=torch.empty(n, device=dev),
                         hp_idx=torch.empty(n, device=dev, dtype=torch.int32),
@@ -557,8 +612,46 @@ class TrainStep:
         # gradient buffers that are accumulated into
         plan.lib.bpb_memset_zero(fl.g.data_ptr(), fl.total * 4, stream)
         plan.lib.bpb_memset_zero(plan.d_emb.data_ptr(), plan.d_emb.numel() * 4, stream)
+        for st, e, de, wgt in plan.sharded:                     # world > 1: all-gather + this rank's anchor rows
+            st.forward(e, plan.pids)
         run(plan.loss_ops)
-        run(plan.bops)
+        for st, e, de, wgt in plan.sharded:                     # gradient of the GLOBAL triplet loss w.r.t. local rows
+            st.backward(wgt, de)
+        if self._world() == 1:
+            run(plan.bops)
+            return
+        # data-parallel: the backward is cut at the stage boundaries; the gradient bucket that is complete after each
+        # segment is all-reduced (NCCL stream) while the next segment's launches run on the compute stream
+        import torch.distributed as dist
+        works, lo_i = [], 0
+        for hi_i, (g_lo, g_hi) in self._buckets(plan):
+            run(plan.bops[lo_i:hi_i])
+            lo_i = hi_i
+            if g_hi > g_lo:
+                works.append(dist.all_reduce(fl.g[g_lo:g_hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w_ in works:
+            w_.wait()
+
+    def _buckets(self, plan):
+        """[(end index into plan.bops, (flat lo, flat hi))]: parameters are laid out in registration order (stem,
+        layer1, transition1, stage2, transition2, stage3, transition3, stage4, incre, head), the backward runs in the
+        opposite order, so each stage boundary closes a contiguous tail of the flat gradient buffer."""
+        if getattr(plan, "_bucket_cache", None) is not None:
+            return plan._bucket_cache
+        fl = self.flat
+        first = {}
+        for name, p, o, n in fl.entries:
+            for st in ("stage2", "stage3", "stage4"):
+                if ("." + st + ".") in ("." + name) and st not in first:
+                    first[st] = o
+        out, hi = [], fl.total
+        for idx, st in plan.marks:                               # backward order: stage4, stage3, stage2
+            if st in first:
+                out.append((idx, (first[st], hi)))
+                hi = first[st]
+        out.append((len(plan.bops), (0, hi)))
+        plan._bucket_cache = out
+        return out
 
     def _optimizer(self, plan):
         fl = self.flat
@@ -594,10 +687,7 @@ class TrainStep:
                 self.graphs[key] = g
             self.graphs[key].replay()
         else:
-            self._launch(plan)
-        if self._world() > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat.g, op=dist.ReduceOp.SUM, group=self.group)
+            self._launch(plan)                                  # (world > 1: gradient all-reduce inside, bucketed)
         return plan
 
     def step(self, images, pids, masks=None):
@@ -617,3 +707,38 @@ class TrainStep:
                 continue
             out[name] = fl.conv_grad_view(conv_w[id(p)]) if id(p) in conv_w else fl.grad_view(p)
         return out
+
+
+class _PublishGrads(torch.autograd.Function):
+    """loss tensor whose .backward() publishes the gradients the fused step already computed (scaled by grad_output)
+    into the parameters' .grad -- so `loss.backward(); optimizer.step()` of the reference engine
+    (part_based_engine.py:101-102) keeps working with any torch optimizer."""
+
+    @staticmethod
+    def forward(ctx, loss_value, step, *params):
+        ctx.step = step
+        return loss_value.detach().clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grads = ctx.step.grads()
+        by_id = {id(p): g for (name, p, o, n), g in ((e, grads.get(e[0])) for e in ctx.step.flat.entries) if g is not None}
+        outs = []
+        for p in ctx.step._pub_params:
+            g = by_id.get(id(p))
+            outs.append(None if g is None else g * grad_out)
+        return (None, None, *outs)
+
+
+def autograd_loss(step: TrainStep, images, pids, masks=None, optimizer=None):
+    """forward + loss + analytic backward now; returns a loss tensor that can be `.backward()`-ed like the reference's.
+    With `optimizer` (a torch optimizer over model.parameters()) a post-step hook re-packs the bf16 operand copies."""
+    plan = step.forward_backward(images, pids, masks)
+    params = [p for _, p, _, _ in step.flat.entries if p.requires_grad]
+    step._pub_params = params
+    if optimizer is not None and not getattr(optimizer, "_bpb_hooked", False):
+        def _bump(*_a, **_k):
+            step.model._param_version = getattr(step.model, "_param_version", 0) + 1
+        optimizer.register_step_post_hook(_bump)
+        optimizer._bpb_hooked = True
+    return _PublishGrads.apply(plan.loss_out[0], step, *params)

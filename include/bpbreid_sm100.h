@@ -140,6 +140,15 @@ int bpb_vis_unpack(const int* vis_bits, const float* vis_cont, int n, int kp1, u
 int bpb_triplet_fwd(const float* emb_knd, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
                     float margin, float* dist_nn, float* hp, float* hn, int* hp_idx, int* hn_idx, float* out4,
                     void* stream);
+/* Sharded variant for data-parallel training (one process per GPU): `emb` is the all-gathered tensor in
+ * [shards][K][n_local][D] layout (shards * n_local = n), labels / vis cover all n samples, and only the anchor rows
+ * [row_lo, row_lo + rows) are computed: dist_rows [rows, n], hp/hn/hp_idx/hn_idx [rows] (indices are global).
+ * sums_mode 1: out4 = {sum loss, sum trivial, n_valid, rows} partial sums to all-reduce, then bpb_triplet_finish.
+ * The mined pairs equal those of the reference's gather-on-GPU-0 mining (part_based_engine.py:82-95). */
+int bpb_triplet_fwd_rows(const float* emb, const int64_t* labels, const void* vis, int vis_mode, int n, int k, int d,
+                         float margin, int row_lo, int rows, int n_local, int sums_mode, float* dist_rows, float* hp,
+                         float* hn, int* hp_idx, int* hn_idx, float* out4, void* stream);
+int bpb_triplet_finish(const float* sums4, float* out4, void* stream);
 /* Label-smoothed CE (cross_entropy_loss.py:34-56); scratch has 2n floats; out2 = {loss, top-1 accuracy}.
  * weights NULL: mean over rows; else sum_i CE_i w_i / |w|_1.  acc_mode 1: accuracy over rows with w != 0. */
 int bpb_ce_ls_fwd(const float* logits, int64_t ld, const int64_t* targets, const float* weights, int n, int c,
@@ -229,6 +238,11 @@ int bpb_ce_ls_bwd(const float* logits, int64_t ld, const int64_t* targets, const
 int bpb_triplet_bwd(const float* emb_knd, const void* vis, int vis_mode, const float* hp, const float* hn,
                     const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
                     float loss_weight, float* demb_knd, void* stream);
+/* Sharded variant: anchors [row_lo, row_lo + rows), demb in the same [shards][K][n_local][D] layout as emb (+=);
+ * all-reduce demb across ranks, the rank's own shard is then the gradient of its local embeddings. */
+int bpb_triplet_bwd_rows(const float* emb, const void* vis, int vis_mode, const float* hp, const float* hn,
+                         const int* hp_idx, const int* hn_idx, const float* out4, int n, int k, int d, float margin,
+                         float loss_weight, int row_lo, int rows, int n_local, float* demb, void* stream);
 /* Train-mode nn.BatchNorm1d backward on fp32 [m, c] (bpbreid.py:336-338, 404-409); y != NULL gates by the following
  * ReLU (y = the layer output); dx is written or accumulated; dgamma / dbeta optional. */
 int bpb_bn1d_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ld_x, const float* y, int64_t ld_y,

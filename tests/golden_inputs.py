@@ -164,15 +164,32 @@ def build_product_model(backbone, K, num_classes=751, **over):
                               config=make_cfg(backbone, K, **over))
 
 
-def model_case(name, n=4, num_classes=751):
+def model_case(name, n=None, num_classes=751):
+    """n defaults to 4, and to 16 for the contractive case: its purpose is end-to-end TRAIN-mode comparisons, where the
+    head's BatchNorm1d layers normalise over the batch rows and need more than a handful of samples to be conditioned."""
     from bpbreid_b200 import params
     backbone, K, seed, h, w, ctr = _MODEL_SPECS[name]
+    if n is None:
+        n = 16 if ctr else 4
     m = build_product_model(backbone, K, num_classes)
     sd = params.seeded_state_dict(m, seed)
     if ctr:
         sd = contractive(sd)
     g = torch.Generator().manual_seed(seed + 1)
-    images = torch.randn(n, 3, h, w, generator=g).numpy()
+    images = torch.randn(n, 3, h, w, generator=g)
+    if ctr:
+        # images that DIFFER from each other like photographs do (contrast, colour cast, large-scale structure).  Pure
+        # white noise gives every image the same pooled statistics up to ~1/sqrt(H*W); the train-mode BatchNorm1d layers
+        # of the head then normalise a between-image variation that is smaller than bf16 rounding noise, and any
+        # end-to-end comparison measures that amplification instead of the kernels.
+        scale = 0.4 + 1.6 * torch.rand(n, 1, 1, 1, generator=g)
+        offs = torch.randn(n, 3, 1, 1, generator=g)
+        fy, fx = 0.5 + 2.5 * torch.rand(n, 3, 1, 1, generator=g), 0.5 + 2.5 * torch.rand(n, 3, 1, 1, generator=g)
+        ph = 6.2831853 * torch.rand(n, 3, 1, 1, generator=g)
+        yy = torch.linspace(0, 1, h).view(1, 1, h, 1)
+        xx = torch.linspace(0, 1, w).view(1, 1, 1, w)
+        images = images * scale + offs + 1.5 * torch.sin(6.2831853 * (fy * yy + fx * xx) + ph)
+    images = images.numpy()
     pids = (np.arange(n) // 2).astype(np.int64)
     # external part masks [N, K+1, H/8, W/8] (rows sum to 1, like AddBackgroundMask's softmax, mask_transform.py:81-84)
     masks = torch.softmax(3 * torch.randn(n, K + 1, h // 8, w // 8, generator=g), 1).numpy()

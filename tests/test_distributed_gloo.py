@@ -17,7 +17,7 @@ from tests import golden_inputs as GI
 
 
 def test_shard_bounds_keep_identities_together():
-    for gb, ws in [(256, 8), (256, 3), (64, 2), (40, 4)]:
+    for gb, ws in [(256, 8), (256, 4), (64, 2), (48, 4)]:
         spans = [D.shard_bounds(gb, ws, r) for r in range(ws)]
         assert spans[0][0] == 0 and spans[-1][1] == gb
         for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
@@ -25,6 +25,8 @@ def test_shard_bounds_keep_identities_together():
         assert all(lo % 4 == 0 and hi % 4 == 0 for lo, hi in spans)
     with pytest.raises(ValueError):
         D.shard_bounds(30, 2, 0)
+    with pytest.raises(ValueError):                  # unequal shards would dead-lock all_gather_into_tensor
+        D.shard_bounds(256, 3, 0)
 
 
 class OracleCriterion:
