@@ -134,27 +134,7 @@ def contractive(sd):
     return out
 
 
-class _Cfg(dict):
-    def __getattr__(self, k):
-        try:
-            return self[k]
-        except KeyError as e:
-            raise AttributeError(k) from e
-
-    def __setattr__(self, k, v):
-        self[k] = v
-
-
-def make_cfg(backbone="hrnet32", parts_num=5, **over):
-    """cfg.model.bpbreid node with the reference's defaults (torchreid/scripts/default_config.py:45-58)."""
-    b = _Cfg(pooling="gwap", normalization="identity", mask_filtering_training=False, mask_filtering_testing=True,
-             last_stride=1, dim_reduce="after_pooling", dim_reduce_output=512, backbone=backbone,
-             learnable_attention_enabled=True, test_embeddings=["bn_foreg", "parts"],
-             test_use_target_segmentation="none", training_binary_visibility_score=True,
-             testing_binary_visibility_score=True, shared_parts_id_classifier=False, hrnet_pretrained_path="",
-             masks=_Cfg(parts_num=parts_num))
-    b.update(over)
-    return _Cfg(model=_Cfg(bpbreid=b))
+from bpbreid_b200.config import Cfg as _Cfg, make_cfg  # noqa: E402,F401  (one definition of the reference defaults)
 
 
 def build_product_model(backbone, K, num_classes=751, **over):
