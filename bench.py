@@ -341,14 +341,14 @@ class FwdLoss:
 class TrainRun:
     """fwd + loss + analytic backward + Adam (bpbreid_b200.train.TrainStep)."""
 
-    def __init__(self, dev, batch, h, rank, world):
+    def __init__(self, dev, batch, h, rank, world, use_graph=True):
         from bpbreid_b200 import losses, models, train
         torch.manual_seed(0)
         self.model = models.build_model("bpbreid", num_classes=NUM_CLASSES, loss="part_based", pretrained=False,
                                         use_gpu=True, config=make_cfg()).to(dev)
         self.model.materialize_spatial_features = False
         crit = losses.GiLtLoss(None, use_visibility_scores=False, triplet_margin=0.3, use_gpu=True)
-        self.ts = train.TrainStep(self.model, crit, None, use_graph=True)
+        self.ts = train.TrainStep(self.model, crit, None, use_graph=use_graph)
         images_h, pids_h = synth_batch(batch, 1 + rank, h, 128)
         self.pids = ((pids_h + rank * (batch // 4)) % NUM_CLASSES).to(dev)
         self.images_h = images_h
@@ -461,7 +461,7 @@ def run_gpu_arm(args, rank, world):
             dist.destroy_process_group()
         return
 
-    runner = (TrainRun if args.workload == "train" else FwdLoss)(dev, per_gpu, h, rank, world)
+    runner = (TrainRun if args.workload == "train" else FwdLoss)(dev, per_gpu, h, rank, world, not args.no_graph)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sampler = ClockSampler(local)
     if args.profile:
@@ -585,6 +585,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling) or global batch (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly (kernel-by-kernel profiling)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-library", action="store_true")
     ap.add_argument("--profile", action="store_true",

@@ -249,7 +249,7 @@ int bpb_conv_wgrad_bf16(const void* x, const void* dy, float* dw, int n, int h, 
 int bpb_relu_grad_sum(const void* const* srcs, int nsrc, const void* y, void* out, int64_t m, int c, void* stream) {
     return relu_grad_sum(srcs, nsrc, y, out, m, c, S(stream));
 }
-int64_t bpb_bn_bwd_workspace_bytes(int c) { return static_cast<int64_t>(c) * 2 * 8 + 16; }
+int64_t bpb_bn_bwd_workspace_bytes(int c) { return bn_bwd_workspace_bytes(c); }
 int bpb_bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
                       int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,
                       float* dgamma, float* dbeta, void* stream) {

@@ -117,7 +117,7 @@ __device__ __forceinline__ void bn_bwd_load_g(const BnBwdArgs& a, unsigned r, in
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, double* __restrict__ ws,
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, float* __restrict__ ws,
                                                             unsigned int* __restrict__ counter, double inv_count,
                                                             float* __restrict__ coef, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta) {
@@ -152,17 +152,41 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, double*
             }
         }
     }
+    // block reduction over the row lanes: threads that share a channel vector are `width` apart.  Inside a warp that is a
+    // shuffle tree (a serial loop over up to 64 row lanes on `width` threads cost more than the whole HBM pass for the
+    // narrow C = 32 / 64 layers); across warps one pass over at most 8 partial rows in shared memory.
+    if (width < 32) {
+        for (int off = width; off < 32; off <<= 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { red[0][threadIdx.x][j] = s[j]; red[1][threadIdx.x][j] = q[j]; }
+            for (int j = 0; j < 8; ++j) {
+                s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+                q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int parts = width < 32 ? 8 : rows_per_block;       // partial rows to add up (one per warp / per row lane)
+    if (width < 32) {
+        if (lane < width) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { red[0][wrp * width + lane][j] = s[j]; red[1][wrp * width + lane][j] = q[j]; }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[0][threadIdx.x][j] = s[j]; red[1][threadIdx.x][j] = q[j]; }
+    }
     __syncthreads();
-    if (ty == 0 && cv < a.cvec) {
-        for (int l = 1; l < rows_per_block; ++l)
+    if (threadIdx.x < width && cv < a.cvec) {               // row 0 of the partials is this thread's own register total
+        for (int l = 1; l < parts; ++l)
 #pragma unroll
             for (int j = 0; j < 8; ++j) { s[j] += red[0][l * width + tx][j]; q[j] += red[1][l * width + tx][j]; }
+        // one row of per-block partials (no atomics: ~1200 blocks adding into the same few cache lines serialised at
+        // the L2 and made this kernel slower than the HBM pass it does)
+        float* mine = ws + static_cast<size_t>(blockIdx.x) * 2 * c;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            atomicAdd(ws + cv * 8 + j, static_cast<double>(s[j]));
-            atomicAdd(ws + c + cv * 8 + j, static_cast<double>(q[j]));
+            mine[cv * 8 + j] = s[j];
+            mine[c + cv * 8 + j] = q[j];
         }
     }
     __threadfence();
@@ -172,7 +196,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, double*
     if (s_is_last) {
         __threadfence();
         for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-            const double sg = __ldcg(ws + ch), sgx = __ldcg(ws + c + ch);
+            double sg = 0.0, sgx = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) {
+                sg += static_cast<double>(__ldcg(ws + static_cast<size_t>(b) * 2 * c + ch));
+                sgx += static_cast<double>(__ldcg(ws + static_cast<size_t>(b) * 2 * c + c + ch));
+            }
             coef[ch] = static_cast<float>(sg * inv_count);
             coef[c + ch] = static_cast<float>(sgx * inv_count);
             const int pc = ch - a.c_lo;
@@ -180,8 +208,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, double*
                 if (dbeta) dbeta[pc] = static_cast<float>(sg);
                 if (dgamma) dgamma[pc] = static_cast<float>(sgx);
             }
-            ws[ch] = 0.0;
-            ws[c + ch] = 0.0;
         }
         if (threadIdx.x == 0) *counter = 0u;
     }
@@ -236,6 +262,8 @@ static int bn_bwd_grid(int64_t m, int cvec) {
     return blocks;
 }
 
+constexpr int kBnRedBlocks = 148 * 2;      // reduce pass: one partial row per block, summed by the last block
+
 int bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
                   int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,
                   float* dgamma, float* dbeta, cudaStream_t stream) {
@@ -243,11 +271,12 @@ int bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, con
     BPB_CHECK(up_log2 >= 0 && up_log2 <= 3, "bn_bwd_reduce: up_log2=%d", up_log2);
     BnBwdArgs a{reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(raw), mean_invstd, scale, shift,
                 n, h, w, c / 8, up_log2, relu_affine, c_lo};
-    double* ws = reinterpret_cast<double*>(workspace);
-    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + 2 * static_cast<size_t>(c));
+    float* ws = reinterpret_cast<float*>(workspace);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + static_cast<size_t>(kBnRedBlocks) * 2 * c);
     const int64_t m = static_cast<int64_t>(n) * h * w;
-    bn_bwd_reduce_kernel<<<bn_bwd_grid(m, c / 8), 256, 0, stream>>>(a, ws, counter, 1.0 / static_cast<double>(m), coef,
-                                                                    dgamma, dbeta);
+    int blocks = bn_bwd_grid(m, c / 8);
+    if (blocks > kBnRedBlocks) blocks = kBnRedBlocks;
+    bn_bwd_reduce_kernel<<<blocks, 256, 0, stream>>>(a, ws, counter, 1.0 / static_cast<double>(m), coef, dgamma, dbeta);
     BPB_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     return 0;
 }
@@ -263,6 +292,8 @@ int bn_bwd_apply(const void* dy, const void* raw, const float* mean_invstd, cons
     BPB_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return 0;
 }
+
+int64_t bn_bwd_workspace_bytes(int c) { return static_cast<int64_t>(kBnRedBlocks) * 2 * c * 4 + 16; }
 
 // ----------------------------------------------------------------------------------------------
 // Stem weight gradient (3 -> 64 channels, NCHW fp32 image, PyTorch weight layout [64][3][k][k]):

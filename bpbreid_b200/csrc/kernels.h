@@ -120,6 +120,7 @@ int relu_grad_sum(const void* const* srcs, int nsrc, const void* y, void* out, i
 int bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
                   int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,
                   float* dgamma, float* dbeta, cudaStream_t stream);
+int64_t bn_bwd_workspace_bytes(int c);
 int bn_bwd_apply(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
                  const float* coef, int n, int h, int w, int c, int up_log2, int relu_affine, int zero_insert,
                  void* draw, cudaStream_t stream);

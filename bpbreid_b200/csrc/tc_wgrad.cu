@@ -16,11 +16,18 @@
 //     tap group (zero padding = TMA out-of-bounds fill, stride 2 = tensor-map element strides).
 // dY may be stored zero-inserted ([N, 2Ho, 2Wo, C], the layout the stride-2 dgrad consumes): it is then read through
 // element strides of 2, so that layout is written once and read by both backward kernels.
+// 3x3 stride-1 layers whose chunk lies inside one image use the forward kernel's "row shift" schedule: a tap group is one
+// HORIZONTAL tap; a single (rows+2)-row input box per chunk serves the three vertical taps, entered r*Wo pixel rows
+// further down the tile (whole 8-row swizzle atoms: the MN-major descriptor just gets a new start address).  The
+// kernel is bound by the L2 -> SM operand stream (measured 6.9 TB/s on the C=32 layers with one box per tap); this
+// cuts that stream 1.6x.
 // Grid: (cout tiles x cin tiles x tap groups) x K splits; every CTA adds its partial tile to the fp32 OHWI gradient
 // with 16-byte vector reductions (red.global.add.v4.f32).  Channel counts < 128 on the M side replicate the channel
 // block (descriptor LBO = 0): the duplicate accumulator rows are simply not read back.
 //
-// Roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 epilogue.
+// Roles (32 * (1 + taps + 4) threads): warp 0 TMA producer; warps 1..taps MMA issuers, ONE PER FILTER TAP of the group
+// (a single thread can start a tcgen05.mma only every ~100 cycles, tools/micro/umma_rate.cu, and every tap has its own
+// TMEM accumulator, so the taps issue concurrently: 24 -> 8 dependent issues per 128-pixel chunk); 4 epilogue warps.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -38,6 +45,10 @@ struct WgradParams {
     int co_tiles, ci_tiles;
     int chunks, ksplit, stages;
     int dy_up;                    // dY stored zero-inserted (2x)
+    int rowshift;                 // 3x3 stride-1, chunk inside one image: group = horizontal tap, ONE (bh+2)-row input box
+                                  // per chunk feeds the three vertical taps through K-axis (pixel-row) start offsets
+    int b_stage_bytes;            // bytes of the input-operand part of a stage
+    int b_tap_stride;             // bytes between the operands of consecutive taps of the group inside a stage
     int tmem_cols;
     float* dw;                    // [cout][ksize*ksize][cin] fp32
 };
@@ -59,7 +70,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 template <int CIT>
-__global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY,
+__global__ void __launch_bounds__(256) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY,
                                                        const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -69,7 +80,7 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int a_box_bytes = 128 * p.a_row_bytes, b_box_bytes = 128 * p.b_row_bytes;
     const int a_bytes = p.a_blocks * a_box_bytes;
-    const int stage_bytes = a_bytes + p.taps_g * b_box_bytes;
+    const int stage_bytes = a_bytes + p.b_stage_bytes;
 
     // tile coordinates
     int t = blockIdx.x;
@@ -83,8 +94,8 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
     const uint32_t smem_a = smem_u32(smem);
     const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]), accf_a = smem_u32(&acc_full);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&acc_full, 1);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.taps_g); }
+        mbar_init(&acc_full, p.taps_g);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmX); }
@@ -110,26 +121,32 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
                 mbar_expect_tx_a(fb, stage_bytes);
                 for (int b = 0; b < p.a_blocks; ++b)
                     tma_load_4d_a(dst + b * a_box_bytes, &tmY, fb, co0 + b * a_elems, 0, h0 * e, n0);
-                for (int tt = 0; tt < p.taps_g; ++tt) {
-                    const int tap = grp * p.taps_g + tt;
-                    const int r = tap / p.ksize, sx = tap - r * p.ksize;
-                    tma_load_4d_a(dst + a_bytes + tt * b_box_bytes, &tmX, fb, ci0, sx - p.pad,
-                                  h0 * p.stride + r - p.pad, n0);
+                if (p.rowshift) {
+                    tma_load_4d_a(dst + a_bytes, &tmX, fb, ci0, grp - 1, h0 - 1, n0);
+                } else {
+                    for (int tt = 0; tt < p.taps_g; ++tt) {
+                        const int tap = grp * p.taps_g + tt;
+                        const int r = tap / p.ksize, sx = tap - r * p.ksize;
+                        tma_load_4d_a(dst + a_bytes + tt * b_box_bytes, &tmX, fb, ci0, sx - p.pad,
+                                      h0 * p.stride + r - p.pad, n0);
+                    }
                 }
             }
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-    } else if (warp == 1) {
-        // ------------------------------ MMA issuer ------------------------------
+    } else if (warp <= p.taps_g) {
+        // ------------------------------ MMA issuers: warp 1 + t owns filter tap t of the group ------------------------
         // instruction descriptor: bf16 x bf16 -> fp32, M = 128, N = CIT, both operands MN-major (bits 15 / 16)
         constexpr uint32_t idesc = make_idesc(false, 128, CIT) | (1u << 15) | (1u << 16);
         const bool leader = elect_one_sync();
+        const int tt = warp - 1;
         const uint32_t lbo_a = p.a_blocks > 1 ? static_cast<uint32_t>(a_box_bytes) : 0u;   // 0: replicate the channel block
         const uint64_t da_hi = make_mnmajor_desc(0, p.a_row_bytes, lbo_a);
         const uint64_t db_hi = make_mnmajor_desc(0, p.b_row_bytes, 0);
         const uint32_t kstep_a = static_cast<uint32_t>(16 * p.a_row_bytes) >> 4;          // 16 pixels per MMA
         const uint32_t kstep_b = static_cast<uint32_t>(16 * p.b_row_bytes) >> 4;
+        const uint32_t tacc = tmem_base + tt * CIT;
         int s = 0;
         uint32_t ph = 0;
         for (int c = c_begin; c < c_end; ++c) {
@@ -138,14 +155,11 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
             tc_fence_after();
             if (leader) {
                 const uint64_t da = da_hi | static_cast<uint64_t>((stage & 0x3FFFFu) >> 4);
-                for (int tt = 0; tt < p.taps_g; ++tt) {
-                    const uint64_t db = db_hi | static_cast<uint64_t>(((stage + a_bytes + tt * b_box_bytes) & 0x3FFFFu) >> 4);
+                const uint64_t db = db_hi | static_cast<uint64_t>(((stage + a_bytes + tt * p.b_tap_stride) & 0x3FFFFu) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma<false>(tmem_base + tt * CIT, da + k * kstep_a, db + k * kstep_b, idesc,
-                                    (c > c_begin || k > 0) ? 1u : 0u);
-                }
-                umma_commit_a(empty_a + s * 8);
+                for (int k = 0; k < 8; ++k)
+                    umma<false>(tacc, da + k * kstep_a, db + k * kstep_b, idesc, (c > c_begin || k > 0) ? 1u : 0u);
+                umma_commit_a(empty_a + s * 8);               // the slot is free once every tap's MMAs have retired
                 if (c == c_end - 1) umma_commit_a(accf_a);
             }
             __syncwarp();
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ C
         const bool row_ok = row < p.cot;                     // rows >= cot are replicas of the channel block
         float* wrow = p.dw + (static_cast<size_t>(co0 + row) * taps) * p.cin + ci0;
         for (int tt = 0; tt < p.taps_g; ++tt) {
-            const int tap = grp * p.taps_g + tt;
+            const int tap = p.rowshift ? tt * 3 + grp : grp * p.taps_g + tt;
 #pragma unroll
             for (int c0 = 0; c0 < CIT; c0 += 16) {
                 uint32_t v[16];
@@ -213,6 +227,9 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dw, int n, int h, int wd
     p.chunks = ((n + bnimg - 1) / bnimg) * p.tpg;
     p.dy_up = dy_up ? 1 : 0;
     p.dw = dw;
+    p.rowshift = (ksize == 3 && stride == 1 && bnimg == 1 && wo % 8 == 0 && !dy_up) ? 1 : 0;
+    p.b_stage_bytes = p.rowshift ? (128 + 2 * wo) * p.b_row_bytes : p.taps_g * 128 * p.b_row_bytes;
+    p.b_tap_stride = p.rowshift ? wo * p.b_row_bytes : 128 * p.b_row_bytes;
     const int tiles = p.co_tiles * p.ci_tiles * p.groups;
     const int num_sms = device_sm_count();
     if (num_sms <= 0) return 2;
@@ -220,7 +237,7 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dw, int n, int h, int wd
     if (ksplit > p.chunks) ksplit = p.chunks;
     if (ksplit < 1) ksplit = 1;
     p.ksplit = ksplit;
-    const int stage_bytes = p.a_blocks * 128 * p.a_row_bytes + p.taps_g * 128 * p.b_row_bytes;
+    const int stage_bytes = p.a_blocks * 128 * p.a_row_bytes + p.b_stage_bytes;
     int stages = (100 * 1024) / stage_bytes;                 // ~100 KB of ring -> two CTAs per SM
     if (stages > 6) stages = 6;
     if (stages < 2) stages = 2;
@@ -242,7 +259,8 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dw, int n, int h, int wd
     {
         uint64_t dims[4] = {(uint64_t)cin, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
         uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)wd * cin * 2, (uint64_t)h * wd * cin * 2};
-        uint32_t box[4] = {(uint32_t)p.cit, (uint32_t)(wo * stride), (uint32_t)(bh * stride), (uint32_t)bnimg};
+        uint32_t box[4] = {(uint32_t)p.cit, (uint32_t)(wo * stride), (uint32_t)((p.rowshift ? bh + 2 : bh) * stride),
+                           (uint32_t)bnimg};
         uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         if (make_tensor_map(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box, es,
                             p.b_row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return 4;
@@ -251,10 +269,10 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dw, int n, int h, int wd
     dim3 grid(tiles, ksplit);
     if (p.cit == 32) {
         BPB_SET_MAX_SMEM(tc_wgrad_kernel<32>, 200 * 1024);
-        tc_wgrad_kernel<32><<<grid, 192, smem, stream>>>(tmY, tmX, p);
+        tc_wgrad_kernel<32><<<grid, 32 * (5 + p.taps_g), smem, stream>>>(tmY, tmX, p);
     } else {
         BPB_SET_MAX_SMEM(tc_wgrad_kernel<64>, 200 * 1024);
-        tc_wgrad_kernel<64><<<grid, 192, smem, stream>>>(tmY, tmX, p);
+        tc_wgrad_kernel<64><<<grid, 32 * (5 + p.taps_g), smem, stream>>>(tmY, tmX, p);
     }
     BPB_LAUNCH_CHECK("tc_wgrad_kernel");
     return 0;

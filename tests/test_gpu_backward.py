@@ -152,7 +152,7 @@ def test_bn_backward_kernels(cfg):
     else:
         got = out.float()
     assert relmax(got, xr.grad) < 1e-2
-    assert int(ws.view(torch.int32).abs().sum()) == 0
+    assert int(ws[-16:].view(torch.int32).abs().sum()) == 0       # the launch counter is left at zero
 
 
 def test_relu_grad_sum_and_transpose():
