@@ -36,13 +36,13 @@ _SIGS = {
     "bpb_instnorm_stats": [_P, _P, _I, _I, _I, _I, _I, _F, _P],
     "bpb_ibn_apply": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "bpb_pixel_fold": [_P, _P, _P, _P, _I, _I, _P, _P, _P],
-    "bpb_pixel_classify": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "bpb_pixel_classify": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     "bpb_part_pool": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
     "bpb_linear_tf32": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bpb_bn1d": [_P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _P],
     "bpb_head_branch_stats": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P],
     "bpb_head_lowres_logits": [_P, _P, _L, _I, _I, _I, _I, _P, _P],
-    "bpb_head_pixel": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "bpb_head_pixel": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "bpb_head_branch_pool": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "bpb_vis_unpack": [_P, _P, _I, _I, _P, _P, _P],
     "bpb_weighted_sum": [_P, _P, _I, _P, _P],
@@ -57,6 +57,7 @@ _SIGS = {
     "bpb_rank_market1501": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "bpb_argsort_rows": [_P, _I, _I, _P, _P],
     "bpb_l2_normalize": [_P, _P, _L, _I, _F, _P],
+    "bpb_resize_bilinear_f32": [_P, _P, _L, _I, _I, _I, _I, _P],
     "bpb_conv_wgrad_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpb_relu_grad_sum": [_P, _I, _P, _P, _L, _I, _P],
     "bpb_bn_bwd_workspace_bytes": [_I],

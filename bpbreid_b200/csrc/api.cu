@@ -157,8 +157,9 @@ int bpb_pixel_fold(const float* w, const float* b, const float* scale, const flo
 }
 int bpb_pixel_classify(const void* feats, const float* wf, const float* bf, int n, int hw, int c, int kp1,
                        float* logits_nchw, float* probs, float* fg_mask, int* vis_bits, float* vis_cont,
-                       void* stream) {
-    return pixel_classify(feats, wf, bf, n, hw, c, kp1, logits_nchw, probs, fg_mask, vis_bits, vis_cont, S(stream));
+                       const float* ext_masks, int mode, void* stream) {
+    return pixel_classify(feats, wf, bf, n, hw, c, kp1, logits_nchw, probs, fg_mask, vis_bits, vis_cont, ext_masks, mode,
+                          S(stream));
 }
 int bpb_part_pool(const void* feats, const float* probs, const float* fg_mask, int n, int hw, int c, int kp1,
                   float* pooled, void* stream) {
@@ -183,9 +184,9 @@ int bpb_head_lowres_logits(const void* x, const float* wf, int64_t rows, int cb,
 }
 int bpb_head_pixel(const float* const* lowres_logits, float* const* mask_t, const int* hb, const int* wb, int nb,
                    const float* bf, int n, int h, int w, int kp1, float* logits, float* probs, float* fg_mask,
-                   int* vis_bits, float* vis_cont, float* mask_sum, void* stream) {
+                   int* vis_bits, float* vis_cont, float* mask_sum, const float* ext_masks, int mode, void* stream) {
     return head_pixel(lowres_logits, mask_t, hb, wb, nb, bf, n, h, w, kp1, logits, probs, fg_mask, vis_bits, vis_cont,
-                      mask_sum, S(stream));
+                      mask_sum, ext_masks, mode, S(stream));
 }
 int bpb_head_branch_pool(const void* x, const float* mt, const float* mask_sum, int n, int q, int cb, int c_off,
                          int ctot, int kp1, int hw_full, float* pooled, void* stream) {
@@ -336,6 +337,9 @@ int bpb_head_branch_bwd(const void* x, const float* mt, const float* gs, const f
     return head_branch_bwd(x, mt, gs, dlow, wf, coefab, n, hb, wb, cb, c_off, ctot, h, w, kp1, dx, S(stream));
 }
 
+int bpb_resize_bilinear_f32(const float* in, float* out, int64_t planes, int hi, int wi, int ho, int wo, void* stream) {
+    return resize_bilinear_f32(in, out, planes, hi, wi, ho, wo, S(stream));
+}
 int bpb_l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, void* stream) {
     return l2_normalize(x, y, rows, d, eps, S(stream));
 }

@@ -340,6 +340,32 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// Mask algebra of BPBreID.forward for externally supplied part masks (torchreid/models/bpbreid.py:157-175).
+//   pr[]  in: per-pixel attention probabilities (softmax of the pixel classifier, or the external masks themselves)
+//         out: the probabilities the VISIBILITY scores are taken from ('hard' rewrites the part entries in place, :167)
+//   pm[]  out: masks used for pooling / returned in the masks dict: pm[0] background, pm[k] part k
+//   ex[]  external masks resized to the feature map (only read when mode & 6)
+template <int KP1>
+__device__ __forceinline__ void apply_target_segmentation(float* pr, float* pm, const float* ex, int mode) {
+#pragma unroll
+    for (int k = 0; k < KP1; ++k) pm[k] = pr[k];
+    if (mode & 2) {                                   // 'hard': keep the parts only where the target segmentation fires
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 1; k < KP1; ++k) mx = fmaxf(mx, ex[k]);
+        const bool target = mx > ex[0];
+        if (!target) {
+#pragma unroll
+            for (int k = 1; k < KP1; ++k) { pr[k] = 1e-12f; pm[k] = 1e-12f; }
+        }
+        pm[0] = target ? 0.f : 1.f;                   // background_masks = ~target_segmentation_mask
+    }
+    if (mode & 4) {                                   // 'soft'
+#pragma unroll
+        for (int k = 1; k < KP1; ++k) pm[k] = pr[k] * ex[k];
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

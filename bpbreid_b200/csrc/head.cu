@@ -40,6 +40,9 @@ int pixel_fold(const float* w, const float* b, const float* scale, const float* 
 
 // ----------------------------------------------------------------------------------------------
 // One warp classifies 4 pixels at a time: logits -> softmax -> masks / visibility.
+// `ext` (optional) = external part masks already resized to the feature map, `mode` bits:
+//   1  external masks ARE the attention (learnable_attention_enabled False, bpbreid.py:149-154): no classifier, no logits
+//   2  test_use_target_segmentation 'hard' (:160-167)     4  'soft' (:169-174)
 // ----------------------------------------------------------------------------------------------
 constexpr int kMaxKp1 = 12;
 constexpr int kPixPerWarp = 4;
@@ -50,9 +53,12 @@ __global__ void __launch_bounds__(256) pixel_classify_kernel(const uint4* __rest
                                                              const float* __restrict__ bf_g, int n, int hw, int c,
                                                              float* __restrict__ logits, float* __restrict__ probs,
                                                              float* __restrict__ fg_mask, int* __restrict__ vis_bits,
-                                                             float* __restrict__ vis_cont) {
+                                                             float* __restrict__ vis_cont,
+                                                             const float* __restrict__ ext, int mode) {
     extern __shared__ float wf[];                     // [KP1][c]
-    for (int i = threadIdx.x; i < KP1 * c; i += blockDim.x) wf[i] = wf_g[i];
+    const bool learn = (mode & 1) == 0;               // mode bit 0: external masks ARE the attention (no classifier)
+    if (learn)
+        for (int i = threadIdx.x; i < KP1 * c; i += blockDim.x) wf[i] = wf_g[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cvec = c / 8;
@@ -65,7 +71,7 @@ __global__ void __launch_bounds__(256) pixel_classify_kernel(const uint4* __rest
         for (int p = 0; p < kPixPerWarp; ++p)
 #pragma unroll
             for (int k = 0; k < KP1; ++k) acc[p][k] = 0.f;
-        for (int cv = lane; cv < cvec; cv += 32) {
+        for (int cv = lane; learn && cv < cvec; cv += 32) {
             float f[kPixPerWarp][8];
 #pragma unroll
             for (int p = 0; p < kPixPerWarp; ++p) {
@@ -95,23 +101,37 @@ __global__ void __launch_bounds__(256) pixel_classify_kernel(const uint4* __rest
             if (lane == p && base + p < total) {
                 const int64_t pix = base + p;
                 const int im = pix / hw, loc = pix % hw;
-                float l[KP1], mx = -INFINITY;
+                float pr[KP1], pm[KP1], ex[KP1];
+                if (ext != nullptr) {
 #pragma unroll
-                for (int k = 0; k < KP1; ++k) { l[k] = acc[p][k] + bf_g[k]; mx = fmaxf(mx, l[k]); }
-                float e[KP1], den = 0.f;
+                    for (int k = 0; k < KP1; ++k) ex[k] = ext[(static_cast<int64_t>(im) * KP1 + k) * hw + loc];
+                }
+                if (learn) {
+                    float l[KP1], mx = -INFINITY;
 #pragma unroll
-                for (int k = 0; k < KP1; ++k) { e[k] = expf(l[k] - mx); den += e[k]; }
-                const float inv = 1.f / den;
+                    for (int k = 0; k < KP1; ++k) { l[k] = acc[p][k] + bf_g[k]; mx = fmaxf(mx, l[k]); }
+                    float e[KP1], den = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KP1; ++k) { e[k] = expf(l[k] - mx); den += e[k]; }
+                    const float inv = 1.f / den;
+#pragma unroll
+                    for (int k = 0; k < KP1; ++k) {
+                        pr[k] = e[k] * inv;
+                        logits[(static_cast<int64_t>(im) * KP1 + k) * hw + loc] = l[k];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KP1; ++k) pr[k] = ex[k];
+                }
+                apply_target_segmentation<KP1>(pr, pm, ex, mode);
                 int arg = 0;
                 float best = -1.f, fg = -1.f;
 #pragma unroll
                 for (int k = 0; k < KP1; ++k) {
-                    const float pr = e[k] * inv;
-                    logits[(static_cast<int64_t>(im) * KP1 + k) * hw + loc] = l[k];
-                    probs[(static_cast<int64_t>(im) * KP1 + k) * hw + loc] = pr;
-                    if (pr > best) { best = pr; arg = k; }         // first maximum, like torch.argmax
-                    if (k >= 1) fg = fmaxf(fg, pr);
-                    atomicMax(reinterpret_cast<int*>(vis_cont + static_cast<int64_t>(im) * KP1 + k), __float_as_int(pr));
+                    probs[(static_cast<int64_t>(im) * KP1 + k) * hw + loc] = pm[k];
+                    if (pr[k] > best) { best = pr[k]; arg = k; }   // first maximum, like torch.argmax
+                    if (k >= 1) fg = fmaxf(fg, pm[k]);
+                    atomicMax(reinterpret_cast<int*>(vis_cont + static_cast<int64_t>(im) * KP1 + k), __float_as_int(pr[k]));
                 }
                 fg_mask[pix] = fg;
                 atomicOr(vis_bits + im, 1 << arg);
@@ -121,8 +141,9 @@ __global__ void __launch_bounds__(256) pixel_classify_kernel(const uint4* __rest
 }
 
 int pixel_classify(const void* feats, const float* wf, const float* bf, int n, int hw, int c, int kp1,
-                   float* logits_nchw, float* probs, float* fg_mask, int* vis_bits, float* vis_cont,
-                   cudaStream_t stream) {
+                   float* logits_nchw, float* probs, float* fg_mask, int* vis_bits, float* vis_cont, const float* ext,
+                   int mode, cudaStream_t stream) {
+    BPB_CHECK(mode == 0 || ext != nullptr, "pixel_classify: mode %d needs the external masks", mode);
     BPB_CHECK(c % 8 == 0, "pixel_classify: C=%d must be a multiple of 8", c);
     BPB_CHECK(kp1 >= 2 && kp1 <= kMaxKp1, "pixel_classify: K+1=%d out of range [2,%d]", kp1, kMaxKp1);
     BPB_CUDA(cudaMemsetAsync(vis_bits, 0, sizeof(int) * n, stream));
@@ -136,7 +157,7 @@ int pixel_classify(const void* feats, const float* wf, const float* bf, int n, i
         auto kern = pixel_classify_kernel<K>;                                                                       \
         BPB_SET_MAX_SMEM(kern, 160 * 1024);                                                                                                           \
         kern<<<blocks, 256, smem, stream>>>(reinterpret_cast<const uint4*>(feats), wf, bf, n, hw, c, logits_nchw,   \
-                                            probs, fg_mask, vis_bits, vis_cont);                                    \
+                                            probs, fg_mask, vis_bits, vis_cont, ext, mode);                         \
         break;                                                                                                      \
     }
     switch (kp1) {

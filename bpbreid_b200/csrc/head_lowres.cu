@@ -235,8 +235,10 @@ template <int KP1>
 __global__ void __launch_bounds__(256) pixel_head_kernel(BranchGeom g, const float* __restrict__ bf, int h, int w,
                                                          float* __restrict__ logits, float* __restrict__ probs,
                                                          float* __restrict__ fg_mask, int* __restrict__ vis_bits,
-                                                         float* __restrict__ vis_cont, float* __restrict__ mask_sum) {
+                                                         float* __restrict__ vis_cont, float* __restrict__ mask_sum,
+                                                         const float* __restrict__ ext, int mode) {
     constexpr int J = KP1 + 2;
+    const bool learn = (mode & 1) == 0;
     extern __shared__ float acc_mt[];                   // concatenated [J][Q_b] for b = 1..nb-1
     const int n = blockIdx.x;
     const int hw = h * w;
@@ -261,13 +263,16 @@ __global__ void __launch_bounds__(256) pixel_head_kernel(BranchGeom g, const flo
     for (int p = threadIdx.x; p < hw; p += blockDim.x) {
         const int oy = p / w, ox = p % w;
         float l[KP1];
-        const float* l0 = g.lg[0] + (static_cast<int64_t>(n) * hw + p) * KP1;
+        if (learn) {
+            const float* l0 = g.lg[0] + (static_cast<int64_t>(n) * hw + p) * KP1;
 #pragma unroll
-        for (int k = 0; k < KP1; ++k) l[k] = bf[k] + l0[k];
+            for (int k = 0; k < KP1; ++k) l[k] = bf[k] + l0[k];
+        }
         Tap ty[4], tx[4];
         for (int b = 1; b < g.nb; ++b) {
             ty[b] = make_tap(oy, g.hb[b], h);
             tx[b] = make_tap(ox, g.wb[b], w);
+            if (!learn) continue;
             const float* lb = g.lg[b] + static_cast<int64_t>(n) * g.hb[b] * g.wb[b] * KP1;
             const float w00 = (1.f - ty[b].l) * (1.f - tx[b].l), w01 = (1.f - ty[b].l) * tx[b].l;
             const float w10 = ty[b].l * (1.f - tx[b].l), w11 = ty[b].l * tx[b].l;
@@ -278,26 +283,40 @@ __global__ void __launch_bounds__(256) pixel_head_kernel(BranchGeom g, const flo
 #pragma unroll
             for (int k = 0; k < KP1; ++k) l[k] += w00 * a[k] + w01 * bb[k] + w10 * c[k] + w11 * d[k];
         }
-        float mx = -INFINITY;
+        float pr[KP1], pm[KP1], ex[KP1];
+        if (ext != nullptr) {
 #pragma unroll
-        for (int k = 0; k < KP1; ++k) mx = fmaxf(mx, l[k]);
-        float e[KP1], den = 0.f;
+            for (int k = 0; k < KP1; ++k) ex[k] = ext[(static_cast<int64_t>(n) * KP1 + k) * hw + p];
+        }
+        if (learn) {
+            float mx = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < KP1; ++k) { e[k] = expf(l[k] - mx); den += e[k]; }
-        const float inv = 1.f / den;
+            for (int k = 0; k < KP1; ++k) mx = fmaxf(mx, l[k]);
+            float e[KP1], den = 0.f;
+#pragma unroll
+            for (int k = 0; k < KP1; ++k) { e[k] = expf(l[k] - mx); den += e[k]; }
+            const float inv = 1.f / den;
+#pragma unroll
+            for (int k = 0; k < KP1; ++k) {
+                pr[k] = e[k] * inv;
+                logits[(static_cast<int64_t>(n) * KP1 + k) * hw + p] = l[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KP1; ++k) pr[k] = ex[k];
+        }
+        apply_target_segmentation<KP1>(pr, pm, ex, mode);
         float m[J];                                       // mask rows: global, fg, bg, parts
         m[0] = 1.f;
         int arg = 0;
         float best = -1.f, fg = -1.f;
 #pragma unroll
         for (int k = 0; k < KP1; ++k) {
-            const float pr = e[k] * inv;
-            logits[(static_cast<int64_t>(n) * KP1 + k) * hw + p] = l[k];
-            probs[(static_cast<int64_t>(n) * KP1 + k) * hw + p] = pr;
-            if (pr > best) { best = pr; arg = k; }
-            if (k >= 1) fg = fmaxf(fg, pr);
-            vmax[k] = fmaxf(vmax[k], pr);
-            if (k == 0) m[2] = pr; else m[2 + k] = pr;
+            probs[(static_cast<int64_t>(n) * KP1 + k) * hw + p] = pm[k];
+            if (pr[k] > best) { best = pr[k]; arg = k; }
+            if (k >= 1) fg = fmaxf(fg, pm[k]);
+            vmax[k] = fmaxf(vmax[k], pr[k]);
+            if (k == 0) m[2] = pm[k]; else m[2 + k] = pm[k];
         }
         m[1] = fg;
         fg_mask[static_cast<int64_t>(n) * hw + p] = fg;
@@ -349,14 +368,15 @@ __global__ void __launch_bounds__(256) pixel_head_kernel(BranchGeom g, const flo
 
 int head_pixel(const float* const* lowres_logits, float* const* mask_t, const int* hb, const int* wb, int nb,
                const float* bf, int n, int h, int w, int kp1, float* logits, float* probs, float* fg_mask,
-               int* vis_bits, float* vis_cont, float* mask_sum, cudaStream_t stream) {
+               int* vis_bits, float* vis_cont, float* mask_sum, const float* ext, int mode, cudaStream_t stream) {
     BPB_CHECK(nb >= 1 && nb <= 4, "head_pixel: nb=%d", nb);
+    BPB_CHECK(mode == 0 || ext != nullptr, "head_pixel: mode %d needs the external masks", mode);
     BPB_CHECK(hb[0] == h && wb[0] == w, "head_pixel: branch 0 must be at the output resolution");
     BranchGeom g{};
     g.nb = nb;
     size_t smem = 0;
     for (int b = 0; b < nb; ++b) {
-        g.hb[b] = hb[b]; g.wb[b] = wb[b]; g.lg[b] = lowres_logits[b]; g.mt[b] = mask_t[b];
+        g.hb[b] = hb[b]; g.wb[b] = wb[b]; g.lg[b] = lowres_logits ? lowres_logits[b] : nullptr; g.mt[b] = mask_t[b];
         if (b > 0) smem += static_cast<size_t>(kp1 + 2) * hb[b] * wb[b] * sizeof(float);
     }
     BPB_CHECK(smem <= 160 * 1024, "head_pixel: transposed masks do not fit shared memory");
@@ -364,7 +384,8 @@ int head_pixel(const float* const* lowres_logits, float* const* mask_t, const in
     case K: {                                                                                                  \
         auto kern = pixel_head_kernel<K>;                                                                      \
         BPB_SET_MAX_SMEM(kern, 160 * 1024);                                                                                                      \
-        kern<<<n, 256, smem, stream>>>(g, bf, h, w, logits, probs, fg_mask, vis_bits, vis_cont, mask_sum);      \
+        kern<<<n, 256, smem, stream>>>(g, bf, h, w, logits, probs, fg_mask, vis_bits, vis_cont, mask_sum, ext,  \
+                                       mode);                                                                  \
         break;                                                                                                 \
     }
     switch (kp1) {

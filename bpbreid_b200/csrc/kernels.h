@@ -54,8 +54,8 @@ int ibn_apply(const void* x, const float* in_mean_rstd, const float* in_gamma, c
 int pixel_fold(const float* w, const float* b, const float* scale, const float* shift, int kp1, int c, float* wf,
                float* bf, cudaStream_t stream);
 int pixel_classify(const void* feats, const float* wf, const float* bf, int n, int hw, int c, int kp1,
-                   float* logits_nchw, float* probs, float* fg_mask, int* vis_bits, float* vis_cont,
-                   cudaStream_t stream);
+                   float* logits_nchw, float* probs, float* fg_mask, int* vis_bits, float* vis_cont, const float* ext,
+                   int mode, cudaStream_t stream);
 int part_pool(const void* feats, const float* probs, const float* fg_mask, int n, int hw, int c, int kp1,
               float* pooled, cudaStream_t stream);
 int bn1d_train(const float* x, const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
@@ -71,7 +71,7 @@ int head_lowres_logits(const void* x, const float* wf, int64_t rows, int cb, int
                        cudaStream_t stream);
 int head_pixel(const float* const* lowres_logits, float* const* mask_t, const int* hb, const int* wb, int nb,
                const float* bf, int n, int h, int w, int kp1, float* logits, float* probs, float* fg_mask,
-               int* vis_bits, float* vis_cont, float* mask_sum, cudaStream_t stream);
+               int* vis_bits, float* vis_cont, float* mask_sum, const float* ext, int mode, cudaStream_t stream);
 int head_branch_pool(const void* x, const float* mt, const float* mask_sum, int n, int q, int cb, int c_off, int ctot,
                      int kp1, int hw_full, float* pooled, cudaStream_t stream);
 
@@ -166,5 +166,6 @@ int head_branch_bwd(const void* x, const float* mt, const float* gs, const float
 
 // ---- eval_kernels.cu --------------------------------------------------------------------------
 int l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, cudaStream_t stream);
+int resize_bilinear_f32(const float* in, float* out, int64_t planes, int hi, int wi, int ho, int wo, cudaStream_t stream);
 
 }  // namespace bpb

@@ -100,34 +100,56 @@ class ShardedTriplet:
         self.out4 = torch.zeros(4, device=device)
         self.demb_g = torch.zeros(W, K, n, D, device=device)
 
-    def forward(self, emb_knd_local: torch.Tensor, pids_local: torch.Tensor):
-        s = _lib.stream_ptr()
+    # The step is split into kernel phases and NCCL phases so that a caller (bpbreid_b200.train.TrainStep) can capture the
+    # kernel phases in CUDA graphs and issue the collectives between them; forward() / backward() run them back to back.
+    def gather(self, emb_knd_local: torch.Tensor, pids_local: torch.Tensor):
         if self.world > 1:
             dist.all_gather_into_tensor(self.emb_g.view(-1), emb_knd_local.reshape(-1), group=self.group)
             dist.all_gather_into_tensor(self.pids_g, pids_local.contiguous(), group=self.group)
         else:
             self.emb_g.view(-1).copy_(emb_knd_local.reshape(-1))
             self.pids_g.copy_(pids_local)
+
+    def mine(self):
         _lib.call("bpb_triplet_fwd_rows", self.emb_g.data_ptr(), self.pids_g.data_ptr(), None, 0, self.N, self.K, self.D,
                   self.margin, self.rank * self.n, self.n, self.n, 1, self.dist_rows.data_ptr(), self.hp.data_ptr(),
-                  self.hn.data_ptr(), self.hp_idx.data_ptr(), self.hn_idx.data_ptr(), self.sums.data_ptr(), s)
+                  self.hn.data_ptr(), self.hp_idx.data_ptr(), self.hn_idx.data_ptr(), self.sums.data_ptr(),
+                  _lib.stream_ptr())
+
+    def reduce_stats(self):
         if self.world > 1:
             dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
-        _lib.call("bpb_triplet_finish", self.sums.data_ptr(), self.out4.data_ptr(), s)
+
+    def finish(self):
+        _lib.call("bpb_triplet_finish", self.sums.data_ptr(), self.out4.data_ptr(), _lib.stream_ptr())
+
+    def forward(self, emb_knd_local: torch.Tensor, pids_local: torch.Tensor):
+        self.gather(emb_knd_local, pids_local)
+        self.mine()
+        self.reduce_stats()
+        self.finish()
         return self.out4
+
+    def bwd_kernel(self, loss_weight: float):
+        self.demb_g.zero_()
+        _lib.call("bpb_triplet_bwd_rows", self.emb_g.data_ptr(), None, 0, self.hp.data_ptr(), self.hn.data_ptr(),
+                  self.hp_idx.data_ptr(), self.hn_idx.data_ptr(), self.out4.data_ptr(), self.N, self.K, self.D, self.margin,
+                  float(loss_weight), self.rank * self.n, self.n, self.n, self.demb_g.data_ptr(), _lib.stream_ptr())
+
+    def bwd_reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.demb_g, op=dist.ReduceOp.SUM, group=self.group)
+
+    def bwd_copy(self, d_emb_local: torch.Tensor):
+        d_emb_local.view(self.K, self.n, self.D).copy_(self.demb_g[self.rank])
 
     def backward(self, loss_weight: float, d_emb_local: torch.Tensor):
         """d_emb_local [K, n, D] = gradient of loss_weight * loss (the global loss; every rank holds the same value).
         OVERWRITES d_emb_local (a device-to-device copy of this rank's shard of the all-reduced gradient): call it before
         the other contributions are accumulated."""
-        s = _lib.stream_ptr()
-        self.demb_g.zero_()
-        _lib.call("bpb_triplet_bwd_rows", self.emb_g.data_ptr(), None, 0, self.hp.data_ptr(), self.hn.data_ptr(),
-                  self.hp_idx.data_ptr(), self.hn_idx.data_ptr(), self.out4.data_ptr(), self.N, self.K, self.D, self.margin,
-                  float(loss_weight), self.rank * self.n, self.n, self.n, self.demb_g.data_ptr(), s)
-        if self.world > 1:
-            dist.all_reduce(self.demb_g, op=dist.ReduceOp.SUM, group=self.group)
-        d_emb_local.view(self.K, self.n, self.D).copy_(self.demb_g[self.rank])
+        self.bwd_kernel(loss_weight)
+        self.bwd_reduce()
+        self.bwd_copy(d_emb_local)
         return d_emb_local
 
 

@@ -118,12 +118,8 @@ class ImagePartBasedEngine:
         impl = 1 if exact_distance else 0
         dist, part = metrics.part_distance_device(qf, gf, qv, gv, self.dist_combine_strat, dist_metric, impl=impl)
         if rerank:
-            from . import rerank as RR
-            dqq, _ = metrics.part_distance_device(qf, qf, qv, qv, self.dist_combine_strat, dist_metric, impl=impl,
-                                                  want_part_dist=False)
-            dgg, _ = metrics.part_distance_device(gf, gf, gv, gv, self.dist_combine_strat, dist_metric, impl=impl,
-                                                  want_part_dist=False)
-            dist = RR.re_ranking_device(dist, dqq, dgg)
+            raise NotImplementedError("k-reciprocal re-ranking (torchreid/utils/rerank.py:31-113, off by default: "
+                                      "test.rerank False) is outside the hot path built here (SURVEY.md section 8 f3)")
         res = metrics.rank_device(dist, q_pids, g_pids, q_camids, g_camids, max_rank)
         metrics._check_rank(res, dist.shape[1], max_rank)
         self.last_distmat, self.last_body_parts_distmat = dist, part

@@ -80,13 +80,18 @@ class BPBreID(nn.Module):
         self.materialize_spatial_features = True
 
     # -- forward ---------------------------------------------------------------------------------------------
-    def plan_for(self, images):
+    def _needs_masks(self):
+        return (not self.learnable_attention_enabled) or \
+               (not self.training and self.test_use_target_segmentation in ("hard", "soft"))
+
+    def plan_for(self, images, external_parts_masks=None):
         if not images.is_cuda:
             raise RuntimeError("bpbreid_b200.BPBreID runs on sm_100a only: move the model and the images to a CUDA "
                                "device (there is no CPU fallback path)")
         n, _, h, w = images.shape
+        ext_shape = tuple(external_parts_masks.shape) if (self._needs_masks() and external_parts_masks is not None) else None
         key = (n, h, w, self.training, images.device.index, self.conv_impl, self.use_cuda_graph, self.debug_trace,
-               self.lowres_head, self.materialize_spatial_features)
+               self.lowres_head, self.materialize_spatial_features, ext_shape)
         plan = self._plans.get(key)
         if plan is None:
             from .plan import ForwardPlan
@@ -94,18 +99,20 @@ class BPBreID(nn.Module):
             if p0.device != images.device:
                 raise RuntimeError(f"model parameters live on {p0.device}, images on {images.device}")
             plan = ForwardPlan(self, n, h, w, self.training, images.device, self.conv_impl, self.use_cuda_graph,
-                               self.debug_trace)
+                               self.debug_trace, ext_shape=ext_shape)
             self._plans[key] = plan
         return plan
 
     def forward(self, images, external_parts_masks=None):
         if not self.learnable_attention_enabled:
-            assert external_parts_masks is not None
+            assert external_parts_masks is not None                       # bpbreid.py:151
         if not self.training and self.test_use_target_segmentation in ("hard", "soft"):
-            assert external_parts_masks is not None
-            raise NotImplementedError("test_use_target_segmentation != 'none' is not built yet")
-        plan = self.plan_for(images)
-        plan.run(images)
+            assert external_parts_masks is not None                       # bpbreid.py:162,171
+        plan = self.plan_for(images, external_parts_masks)
+        if plan.ext_mode:
+            plan.run(images, external_parts_masks.to(device=images.device, dtype=torch.float32))
+        else:
+            plan.run(images)
         return plan.outputs()
 
     def invalidate_plans(self):

@@ -56,8 +56,19 @@ def _tc_tileable(cin, cout, ho, wo):
 
 class ForwardPlan:
     def __init__(self, model, n, h, w, training, device, conv_impl="tc", use_graph=False, debug=False, grad=False,
-                 flat=None):
+                 flat=None, ext_shape=None):
         self.model = model
+        # external part masks [N, K+1, Hm, Wm] (bpbreid.py:116-175): mode bit 0 = they are the attention
+        # (learnable_attention_enabled False), bit 1 / 2 = test_use_target_segmentation 'hard' / 'soft' (eval only)
+        cfg_ = model.model_cfg
+        self.ext_mode = 0 if cfg_.learnable_attention_enabled else 1
+        if not training and cfg_.test_use_target_segmentation == "hard":
+            self.ext_mode |= 2
+        if not training and cfg_.test_use_target_segmentation == "soft":
+            self.ext_mode |= 4
+        self.ext_shape = ext_shape
+        if self.ext_mode and ext_shape is None:
+            raise AssertionError("external_parts_masks is required by this configuration (bpbreid.py:151,162,171)")
         # gradient mode (bpbreid_b200.train): every activation stays alive for the backward pass, BatchNorm layers
         # save their batch mean / invstd, conv weights come from the flat parameter store's bf16 operand copies
         self.grad = bool(grad)
@@ -481,6 +492,18 @@ class ForwardPlan:
         return x
 
     # ------------------------------------------------------------------ head
+    def _ext_resized(self, h, w):
+        """external masks -> feature-map resolution (recorded resize launch); None when the configuration ignores them"""
+        if not self.ext_mode:
+            return None
+        n, kp1 = self.n, self.K + 1
+        _, c_, hm, wm = self.ext_shape
+        assert c_ == kp1, f"external_parts_masks must have K+1={kp1} channels, got {c_}"
+        self.ext_in = self._small((n, kp1, hm, wm))
+        self.ext_rs = self._small((n, kp1, h, w))
+        self._op("bpb_resize_bilinear_f32", self.ext_in.data_ptr(), self.ext_rs.data_ptr(), n * kp1, hm, wm, h, w)
+        return self.ext_rs
+
     def _alloc_head_outputs(self, h, w, c):
         n, kp1, J = self.n, self.K + 1, self.K + 3
         self.logits = self._small((n, kp1, h, w))
@@ -499,19 +522,23 @@ class ForwardPlan:
         kp1 = self.K + 1
         hw, c = feats.h * feats.w, feats.c
         pc = m.pixel_classifier
-        if self.training:
-            stats, tiles = self.colstats(Act(feats.t, n, feats.h, feats.w, c))
-        else:
-            stats, tiles = None, 0
-        scale, shift = self.bn_scale_shift(stats, tiles, c, n * hw, pc.bn)
-        wf, bf = self._small((kp1, c)), self._small((kp1,))
-        fold = self._op if self.training else self._setup_op
-        fold("bpb_pixel_fold", pc.classifier.weight.data_ptr(), pc.classifier.bias.data_ptr(), scale.data_ptr(),
-             shift.data_ptr(), kp1, c, wf.data_ptr(), bf.data_ptr())
+        learn = (self.ext_mode & 1) == 0
+        wf = bf = None
+        if learn:
+            if self.training:
+                stats, tiles = self.colstats(Act(feats.t, n, feats.h, feats.w, c))
+            else:
+                stats, tiles = None, 0
+            scale, shift = self.bn_scale_shift(stats, tiles, c, n * hw, pc.bn)
+            wf, bf = self._small((kp1, c)), self._small((kp1,))
+            fold = self._op if self.training else self._setup_op
+            fold("bpb_pixel_fold", pc.classifier.weight.data_ptr(), pc.classifier.bias.data_ptr(), scale.data_ptr(),
+                 shift.data_ptr(), kp1, c, wf.data_ptr(), bf.data_ptr())
+        ext = self._ext_resized(feats.h, feats.w)
         self._alloc_head_outputs(feats.h, feats.w, c)
-        self._op("bpb_pixel_classify", feats.t.data_ptr(), wf.data_ptr(), bf.data_ptr(), n, hw, c, kp1,
+        self._op("bpb_pixel_classify", feats.t.data_ptr(), _lib.ptr(wf), _lib.ptr(bf), n, hw, c, kp1,
                  self.logits.data_ptr(), self.probs.data_ptr(), self.fg_mask.data_ptr(), self.vis_bits.data_ptr(),
-                 self.vis_cont.data_ptr())
+                 self.vis_cont.data_ptr(), _lib.ptr(ext), self.ext_mode)
         self._op("bpb_vis_unpack", self.vis_bits.data_ptr(), self.vis_cont.data_ptr(), n, kp1, self.vis_b.data_ptr(),
                  self.vis_f.data_ptr())
         self._op("bpb_part_pool", feats.t.data_ptr(), self.probs.data_ptr(), self.fg_mask.data_ptr(), n, hw, c, kp1,
@@ -527,45 +554,50 @@ class ForwardPlan:
         ctot = sum(b.c for b in br)
         offs = [sum(b.c for b in br[:i]) for i in range(len(br))]
         pc = m.pixel_classifier
-        scale, shift = self._small((ctot,)), self._small((ctot,))
-        if self.training:
-            partial = self._small((n, 2, ctot))
+        learn = (self.ext_mode & 1) == 0
+        scale = shift = wf = bf = None
+        lows = []
+        if learn:
+            scale, shift = self._small((ctot,)), self._small((ctot,))
+            if self.training:
+                partial = self._small((n, 2, ctot))
+                self.fork(range(1, len(br)))
+                for i, (b, off) in enumerate(zip(br, offs)):
+                    with self.lane(i):
+                        self._op("bpb_head_branch_stats", b.t.data_ptr(), n, b.h, b.w, b.c, h, w, partial.data_ptr(), off,
+                                 ctot)
+                self.join()
+                bn = pc.bn
+                mom = bn.momentum if bn.momentum is not None else 0.1
+                self.pix_save = self._small((2, ctot)) if self.grad else None
+                self._op("bpb_bn_finalize", partial.data_ptr(), n, ctot, 0, n * h * w, bn.weight.data_ptr(),
+                         bn.bias.data_ptr(), BN_EPS, float(mom), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                         scale.data_ptr(), shift.data_ptr(), _lib.ptr(self.pix_save))
+            else:
+                self._setup_op("bpb_bn_eval_fold", pc.bn.weight.data_ptr(), pc.bn.bias.data_ptr(),
+                               pc.bn.running_mean.data_ptr(), pc.bn.running_var.data_ptr(), BN_EPS, ctot,
+                               scale.data_ptr(), shift.data_ptr())
+            wf, bf = self._small((kp1, ctot)), self._small((kp1,))
+            fold = self._op if self.training else self._setup_op
+            fold("bpb_pixel_fold", pc.classifier.weight.data_ptr(), pc.classifier.bias.data_ptr(), scale.data_ptr(),
+                 shift.data_ptr(), kp1, ctot, wf.data_ptr(), bf.data_ptr())
+        self._alloc_head_outputs(h, w, ctot)
+        mts = [self._small((n, J, b.h * b.w)) for b in br]
+        if learn:
             self.fork(range(1, len(br)))
             for i, (b, off) in enumerate(zip(br, offs)):
+                lo = self._small((n * b.h * b.w, kp1))
                 with self.lane(i):
-                    self._op("bpb_head_branch_stats", b.t.data_ptr(), n, b.h, b.w, b.c, h, w, partial.data_ptr(), off,
-                             ctot)
+                    self._op("bpb_head_lowres_logits", b.t.data_ptr(), wf.data_ptr(), n * b.h * b.w, b.c, off, ctot, kp1,
+                             lo.data_ptr())
+                lows.append(lo)
             self.join()
-            bn = pc.bn
-            mom = bn.momentum if bn.momentum is not None else 0.1
-            self.pix_save = self._small((2, ctot)) if self.grad else None
-            self._op("bpb_bn_finalize", partial.data_ptr(), n, ctot, 0, n * h * w, bn.weight.data_ptr(),
-                     bn.bias.data_ptr(), BN_EPS, float(mom), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
-                     scale.data_ptr(), shift.data_ptr(), _lib.ptr(self.pix_save))
-        else:
-            self._setup_op("bpb_bn_eval_fold", pc.bn.weight.data_ptr(), pc.bn.bias.data_ptr(),
-                           pc.bn.running_mean.data_ptr(), pc.bn.running_var.data_ptr(), BN_EPS, ctot,
-                           scale.data_ptr(), shift.data_ptr())
-        wf, bf = self._small((kp1, ctot)), self._small((kp1,))
-        fold = self._op if self.training else self._setup_op
-        fold("bpb_pixel_fold", pc.classifier.weight.data_ptr(), pc.classifier.bias.data_ptr(), scale.data_ptr(),
-             shift.data_ptr(), kp1, ctot, wf.data_ptr(), bf.data_ptr())
-        self._alloc_head_outputs(h, w, ctot)
-        lows, mts = [], []
-        self.fork(range(1, len(br)))
-        for i, (b, off) in enumerate(zip(br, offs)):
-            lo = self._small((n * b.h * b.w, kp1))
-            with self.lane(i):
-                self._op("bpb_head_lowres_logits", b.t.data_ptr(), wf.data_ptr(), n * b.h * b.w, b.c, off, ctot, kp1,
-                         lo.data_ptr())
-            lows.append(lo)
-            mts.append(self._small((n, J, b.h * b.w)))
-        self.join()
+        ext = self._ext_resized(h, w)
         self.mask_sum = self._small((n, J))
-        self._op("bpb_head_pixel", self._ptr_array(lows), self._ptr_array(mts), self._int_array([b.h for b in br]),
-                 self._int_array([b.w for b in br]), len(br), bf.data_ptr(), n, h, w, kp1, self.logits.data_ptr(),
-                 self.probs.data_ptr(), self.fg_mask.data_ptr(), self.vis_bits.data_ptr(), self.vis_cont.data_ptr(),
-                 self.mask_sum.data_ptr())
+        self._op("bpb_head_pixel", self._ptr_array(lows) if learn else None, self._ptr_array(mts),
+                 self._int_array([b.h for b in br]), self._int_array([b.w for b in br]), len(br), _lib.ptr(bf), n, h, w, kp1,
+                 self.logits.data_ptr(), self.probs.data_ptr(), self.fg_mask.data_ptr(), self.vis_bits.data_ptr(),
+                 self.vis_cont.data_ptr(), self.mask_sum.data_ptr(), _lib.ptr(ext), self.ext_mode)
         self._op("bpb_vis_unpack", self.vis_bits.data_ptr(), self.vis_cont.data_ptr(), n, kp1, self.vis_b.data_ptr(),
                  self.vis_f.data_ptr())
         self.fork(range(1, len(br)))
@@ -644,8 +676,6 @@ class ForwardPlan:
     def _build(self):
         self.feats = None
         bb = self.model.backbone_appearance_feature_extractor
-        if not self.cfg.learnable_attention_enabled:
-            raise NotImplementedError("external-mask attention (learnable_attention_enabled=False) is not built yet")
         if self.cfg.dim_reduce != "after_pooling" or self.cfg.pooling != "gwap" or self.cfg.normalization != "identity":
             raise NotImplementedError("only the shipped configuration (gwap / identity / after_pooling) is built")
         lowres = getattr(self.model, "lowres_head", True)
@@ -709,7 +739,10 @@ class ForwardPlan:
         for l in active:
             main.wait_stream(streams[l])
 
-    def run(self, images):
+    def run(self, images, external_parts_masks=None):
+        if self.ext_mode:
+            assert external_parts_masks is not None
+            self.ext_in.copy_(external_parts_masks, non_blocking=True)
         ver = getattr(self.model, "_param_version", 0)
         if ver != getattr(self, "_seen_version", 0):          # an optimizer step changed the fp32 masters
             self._seen_version = ver
@@ -758,4 +791,5 @@ class ForwardPlan:
         spatial = None if f is None else f.t.view(n, f.h, f.w, f.c).permute(0, 3, 1, 2)
         masks = {"globl": torch.ones_like(self.fg_mask), "backg": self.probs[:, 0], "foreg": self.fg_mask,
                  "conct": self.fg_mask, "parts": self.probs[:, 1:]}
-        return embeddings, visibility, scores, self.logits, spatial, masks
+        pix = self.logits if (self.ext_mode & 1) == 0 else None     # bpbreid.py:150: no pixel scores without the classifier
+        return embeddings, visibility, scores, pix, spatial, masks

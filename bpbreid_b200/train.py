@@ -608,29 +608,59 @@ class TrainStep:
                 rc = fn(*args, stream)
                 if rc != 0:
                     raise RuntimeError(f"{name} failed (rc={rc}): {err().decode()}")
-        plan._launch_all()                                      # forward (multi-lane)
-        # gradient buffers that are accumulated into
-        plan.lib.bpb_memset_zero(fl.g.data_ptr(), fl.total * 4, stream)
-        plan.lib.bpb_memset_zero(plan.d_emb.data_ptr(), plan.d_emb.numel() * 4, stream)
-        for st, e, de, wgt in plan.sharded:                     # world > 1: all-gather + this rank's anchor rows
-            st.forward(e, plan.pids)
-        run(plan.loss_ops)
-        for st, e, de, wgt in plan.sharded:                     # gradient of the GLOBAL triplet loss w.r.t. local rows
-            st.backward(wgt, de)
         if self._world() == 1:
+            plan._launch_all()                                  # forward (multi-lane)
+            # gradient buffers that are accumulated into
+            plan.lib.bpb_memset_zero(fl.g.data_ptr(), fl.total * 4, stream)
+            plan.lib.bpb_memset_zero(plan.d_emb.data_ptr(), plan.d_emb.numel() * 4, stream)
+            run(plan.loss_ops)
             run(plan.bops)
             return
-        # data-parallel: the backward is cut at the stage boundaries; the gradient bucket that is complete after each
-        # segment is all-reduced (NCCL stream) while the next segment's launches run on the compute stream
+        for kind, fn in self._phases(plan):
+            fn()
+
+    def _phases(self, plan):
+        """Data-parallel step as alternating kernel phases ('g': recorded launches only -- each one is captured in its own
+        CUDA graph by forward_backward) and NCCL phases ('n').  The backward is cut at the stage boundaries; the gradient
+        bucket that is complete after a segment is all-reduced on the NCCL stream while the next segment runs."""
         import torch.distributed as dist
-        works, lo_i = [], 0
+        fl = self.flat
+
+        def run(ops):
+            stream = torch.cuda.current_stream().cuda_stream
+            for fn, args, name in ops:
+                rc = fn(*args, stream)
+                if rc != 0:
+                    raise RuntimeError(f"{name} failed (rc={rc}): {plan.lib.bpb_last_error().decode()}")
+
+        def fwd():
+            stream = torch.cuda.current_stream().cuda_stream
+            plan._launch_all()
+            plan.lib.bpb_memset_zero(fl.g.data_ptr(), fl.total * 4, stream)
+            plan.lib.bpb_memset_zero(plan.d_emb.data_ptr(), plan.d_emb.numel() * 4, stream)
+        works = []
+        ph = [("g", fwd),
+              ("n", lambda: [st.gather(e, plan.pids) for st, e, de, w in plan.sharded]),
+              ("g", lambda: [st.mine() for st, e, de, w in plan.sharded]),
+              ("n", lambda: [st.reduce_stats() for st, e, de, w in plan.sharded]),
+              ("g", lambda: ([st.finish() for st, e, de, w in plan.sharded], run(plan.loss_ops),
+                             [st.bwd_kernel(w) for st, e, de, w in plan.sharded])),
+              ("n", lambda: [st.bwd_reduce() for st, e, de, w in plan.sharded])]
+        lo_i = 0
+        first = True
         for hi_i, (g_lo, g_hi) in self._buckets(plan):
-            run(plan.bops[lo_i:hi_i])
+            seg = plan.bops[lo_i:hi_i]
+            if first:
+                ph.append(("g", lambda seg=seg: ([st.bwd_copy(de) for st, e, de, w in plan.sharded], run(seg))))
+                first = False
+            else:
+                ph.append(("g", lambda seg=seg: run(seg)))
             lo_i = hi_i
             if g_hi > g_lo:
-                works.append(dist.all_reduce(fl.g[g_lo:g_hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        for w_ in works:
-            w_.wait()
+                ph.append(("n", lambda a=g_lo, b=g_hi: works.append(
+                    dist.all_reduce(fl.g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))))
+        ph.append(("n", lambda: ([w_.wait() for w_ in works], works.clear())))
+        return ph
 
     def _buckets(self, plan):
         """[(end index into plan.bops, (flat lo, flat hi))]: parameters are laid out in registration order (stem,
@@ -686,6 +716,26 @@ class TrainStep:
                     self._launch(plan)
                 self.graphs[key] = g
             self.graphs[key].replay()
+        elif self.use_graph:
+            # data parallel: one CUDA graph per kernel phase, the collectives run eagerly between the replays
+            if key not in self.graphs:
+                self._launch(plan)                              # warm-up: kernels AND communicators
+                torch.cuda.synchronize()
+                seq = []
+                for kind, fn in self._phases(plan):
+                    if kind == "g":
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            fn()
+                        seq.append(g.replay)
+                    else:
+                        fn()                                    # keep every rank's collective sequence in step
+                        seq.append(fn)
+                torch.cuda.synchronize()
+                self.graphs[key] = seq
+            else:
+                for fn in self.graphs[key]:
+                    fn()
         else:
             self._launch(plan)                                  # (world > 1: gradient all-reduce inside, bucketed)
         return plan

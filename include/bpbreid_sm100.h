@@ -91,10 +91,14 @@ int bpb_pixel_fold(const float* w, const float* b, const float* scale, const flo
                    float* bf, void* stream);
 /* Pixel classifier + softmax + masks + visibility (bpbreid.py:147-148,157-192).  feats bf16 [n, hw, c].
  * logits/probs fp32 [n, K+1, hw]; fg_mask [n, hw]; vis_bits[n] bit k set iff class k is the argmax somewhere;
- * vis_cont [n, K+1] = amax of the probabilities. */
+ * vis_cont [n, K+1] = amax of the probabilities.
+ * ext_masks (optional): external part masks already resized to the feature map, fp32 [n, K+1, hw]
+ * (bpb_resize_bilinear_f32); mode bit 0: they ARE the attention (learnable_attention_enabled False, bpbreid.py:149-154;
+ * wf / bf / logits unused), bit 1: test_use_target_segmentation 'hard' (:160-167), bit 2: 'soft' (:169-174).
+ * With mode != 0 `probs` holds the masks used for pooling: row 0 background mask, rows 1..K part masks. */
 int bpb_pixel_classify(const void* feats, const float* wf, const float* bf, int n, int hw, int c, int kp1,
                        float* logits_nchw, float* probs, float* fg_mask, int* vis_bits, float* vis_cont,
-                       void* stream);
+                       const float* ext_masks, int mode, void* stream);
 /* Global / foreground / background / K part pooling in one pass (bpbreid.py:195-202,458-503).
  * pooled fp32 [K+3, n, c] with rows {0: global, 1: fg, 2: bg, 3..: parts}. */
 int bpb_part_pool(const void* feats, const float* probs, const float* fg_mask, int n, int hw, int c, int kp1,
@@ -118,10 +122,11 @@ int bpb_head_lowres_logits(const void* x, const float* wf, int64_t rows, int cb,
                            float* out, void* stream);
 /* full-resolution logits = bf + sum_b bilinear(lowres_logits[b]) -> softmax -> masks / visibility (same outputs as
  * bpb_pixel_classify) + mask_sum[n][K+3] and the transposed-upsampled masks mask_t[b][n][K+3][hb*wb]
- * (rows: global, foreground, background, parts). */
+ * (rows: global, foreground, background, parts).  ext_masks / mode as for bpb_pixel_classify (mode bit 0:
+ * lowres_logits may be NULL). */
 int bpb_head_pixel(const float* const* lowres_logits, float* const* mask_t, const int* hb, const int* wb, int nb,
                    const float* bf, int n, int h, int w, int kp1, float* logits, float* probs, float* fg_mask,
-                   int* vis_bits, float* vis_cont, float* mask_sum, void* stream);
+                   int* vis_bits, float* vis_cont, float* mask_sum, const float* ext_masks, int mode, void* stream);
 /* pooled[j][n][c_off+c] = norm_j * sum_q mask_t[n][j][q] x[n][q][c]  (same pooled layout as bpb_part_pool). */
 int bpb_head_branch_pool(const void* x, const float* mt, const float* mask_sum, int n, int q, int cb, int c_off,
                          int ctot, int kp1, int hw_full, float* pooled, void* stream);
@@ -273,6 +278,9 @@ int bpb_head_branch_bwd(const void* x, const float* mt, const float* gs, const f
                         const float* coefab, int n, int hb, int wb, int cb, int c_off, int ctot, int h, int w, int kp1,
                         void* dx, void* stream);
 
+/* out [planes, ho, wo] = bilinear (align_corners=True) resize of in [planes, hi, wi], fp32: nn.functional.interpolate of
+ * the external part masks (bpbreid.py:153, 162-163, 171-172). */
+int bpb_resize_bilinear_f32(const float* in, float* out, int64_t planes, int hi, int wi, int ho, int wo, void* stream);
 /* y[r, :] = x[r, :] / max(|x[r, :]|_2, eps) for `rows` rows of d floats (in place allowed).
  * Replaces Engine.normalize = F.normalize(p=2, dim=-1) (torchreid/engine/engine.py:558-559), applied to the
  * [N, P, D] test embeddings at torchreid/engine/image/part_based_engine.py:205-208. */

@@ -145,6 +145,29 @@ def gen_models(ref, only=None):
         print(f"model_{name}.npz", len(out))
 
 
+def gen_mask_models(ref):
+    """eval-mode outputs of the reference with external part masks (bpbreid.py:149-175)."""
+    from tests.golden_inputs import MASK_CASES, mask_case
+    for name in MASK_CASES:
+        c = mask_case(name)
+        m = ref_loader.build_reference_model(c["backbone"], c["K"], c["num_classes"], **c["over"])
+        m.load_state_dict(c["state_dict"], strict=True)
+        m.eval()
+        with torch.no_grad():
+            emb, vis, ids, pix, feats, masks = m(torch.from_numpy(c["images"]),
+                                                 external_parts_masks=torch.from_numpy(c["masks"]))
+        out = {}
+        for k, v in emb.items():
+            out[f"eval/emb/{k}"] = t2n(v)
+        for k, v in vis.items():
+            out[f"eval/vis/{k}"] = t2n(v)
+        for k, v in masks.items():
+            out[f"eval/masks/{k}"] = t2n(v).astype(np.float32)
+        out["eval/has_pix"] = np.int64(pix is not None)
+        np.savez_compressed(os.path.join(OUT, f"model_{name}.npz"), **out)
+        print(f"model_{name}.npz", len(out))
+
+
 GRAD_FULL_KEYS = ("pixel_classifier.classifier.weight", "pixel_classifier.classifier.bias", "pixel_classifier.bn.weight",
                   "pixel_classifier.bn.bias", "global_identity_classifier.bn.weight",
                   "backbone_appearance_feature_extractor.conv1.weight", "backbone_appearance_feature_extractor.bn1.weight",
@@ -187,7 +210,7 @@ def gen_grads(ref, name="hrnet32_k5_ctr", bpa_weight=0.35):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
-    which = sys.argv[1:] or ["losses", "distance", "rank", "models", "grads"]
+    which = sys.argv[1:] or ["losses", "distance", "rank", "models", "grads", "masks"]
     if "losses" in which:
         gen_losses(ref)
     if "distance" in which:
@@ -201,3 +224,5 @@ if __name__ == "__main__":
         gen_models(ref, only)
     if "grads" in which:
         gen_grads(ref)
+    if "masks" in which:
+        gen_mask_models(ref)

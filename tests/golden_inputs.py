@@ -113,6 +113,12 @@ def rank_case(name):
 
 
 MODEL_CASES = ["hrnet32_k5", "resnet50_k5", "ibn_k8", "hrnet32_k5_384", "hrnet32_k5_ctr"]
+# external part masks (bpbreid.py:149-175): name -> (base case, config overrides); eval-mode goldens with the masks passed
+MASK_CASES = {"hrnet32_k5_extattn": ("hrnet32_k5", dict(learnable_attention_enabled=False)),
+              "hrnet32_k5_hard": ("hrnet32_k5", dict(test_use_target_segmentation="hard")),
+              "hrnet32_k5_soft": ("hrnet32_k5", dict(test_use_target_segmentation="soft")),
+              "resnet50_k5_extattn": ("resnet50_k5", dict(learnable_attention_enabled=False)),
+              "resnet50_k5_soft": ("resnet50_k5", dict(test_use_target_segmentation="soft"))}
 # name -> (backbone, K, seed, H, W, contractive)
 _MODEL_SPECS = {"hrnet32_k5": ("hrnet32", 5, 100, 256, 128, False), "resnet50_k5": ("resnet50", 5, 200, 256, 128, False),
                 "ibn_k8": ("fastreid_resnet_ibn", 8, 300, 256, 128, False),
@@ -144,14 +150,14 @@ def build_product_model(backbone, K, num_classes=751, **over):
                               config=make_cfg(backbone, K, **over))
 
 
-def model_case(name, n=None, num_classes=751):
+def model_case(name, n=None, num_classes=751, **over):
     """n defaults to 4, and to 16 for the contractive case: its purpose is end-to-end TRAIN-mode comparisons, where the
     head's BatchNorm1d layers normalise over the batch rows and need more than a handful of samples to be conditioned."""
     from bpbreid_b200 import params
     backbone, K, seed, h, w, ctr = _MODEL_SPECS[name]
     if n is None:
         n = 16 if ctr else 4
-    m = build_product_model(backbone, K, num_classes)
+    m = build_product_model(backbone, K, num_classes, **over)
     sd = params.seeded_state_dict(m, seed)
     if ctr:
         sd = contractive(sd)
@@ -174,4 +180,9 @@ def model_case(name, n=None, num_classes=751):
     # external part masks [N, K+1, H/8, W/8] (rows sum to 1, like AddBackgroundMask's softmax, mask_transform.py:81-84)
     masks = torch.softmax(3 * torch.randn(n, K + 1, h // 8, w // 8, generator=g), 1).numpy()
     return dict(backbone=backbone, K=K, num_classes=num_classes, state_dict=sd, images=images, pids=pids, model=m,
-                masks=masks)
+                masks=masks, over=over)
+
+
+def mask_case(name):
+    base, over = MASK_CASES[name]
+    return model_case(base, **over)

@@ -359,3 +359,34 @@ def test_map_parity_on_synthetic_gallery_from_model_embeddings(golden):
     r_o = MO.eval_market1501(d_c.cpu().numpy(), pids[q], pids[gal], cams[q], cams[gal], 20)
     np.testing.assert_array_equal(r_c["cmc"], r_o["cmc"])
     assert abs(r_c["mAP"] - r_o["mAP"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", list(GI.MASK_CASES))
+def test_external_part_masks_match_reference_golden(golden, name):
+    """External part masks (bpbreid.py:149-175): attention taken from the masks (learnable_attention_enabled False), and
+    the 'hard' / 'soft' target segmentation of the learned attention at test time -- against the reference's outputs."""
+    g = golden("model_" + name)
+    c = GI.mask_case(name)
+    m = c["model"]
+    m.load_state_dict(c["state_dict"])
+    m = m.to("cuda").eval()
+    x = torch.from_numpy(c["images"]).to("cuda")
+    ext = torch.from_numpy(c["masks"]).to("cuda")
+    with pytest.raises(AssertionError):
+        m(x)                                                   # the reference asserts the masks are there
+    with torch.no_grad():
+        emb, vis, ids, pix, feats, masks = m(x, external_parts_masks=ext)
+    assert (pix is not None) == bool(g["eval/has_pix"])
+    errs = {}
+    for k in ("globl", "foreg", "backg", "parts", "bn_foreg", "bn_parts"):
+        ref = g[f"eval/emb/{k}"]
+        got = emb[k].float().cpu().numpy()
+        errs[k] = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-12))
+    for k in ("backg", "foreg", "parts"):
+        ref = g[f"eval/masks/{k}"]
+        got = masks[k].float().cpu().numpy()
+        errs["mask/" + k] = float(np.abs(got - ref).max() / (np.abs(ref).max() + 1e-12))
+    print(name, errs)
+    assert all(v < 3e-2 for v in errs.values()), errs
+    agree = (vis["parts"].cpu().numpy() == g["eval/vis/parts"]).mean()
+    assert agree > 0.9, agree
