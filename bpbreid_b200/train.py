@@ -733,9 +733,9 @@ class TrainStep:
                         seq.append(fn)
                 torch.cuda.synchronize()
                 self.graphs[key] = seq
-            else:
-                for fn in self.graphs[key]:
-                    fn()
+            # (the collectives issued while capturing ran on stale buffers: the real step is always a full replay)
+            for fn in self.graphs[key]:
+                fn()
         else:
             self._launch(plan)                                  # (world > 1: gradient all-reduce inside, bucketed)
         return plan
