@@ -521,6 +521,27 @@ def run_gpu_arm(args, rank, world):
                 extras["config2_bs64_384x128"] = {"error": repr(e)[:300]}
             torch.cuda.empty_cache()
             try:
+                from bpbreid_b200 import models
+                torch.manual_seed(0)
+                me = models.build_model("bpbreid", num_classes=NUM_CLASSES, loss="part_based", pretrained=False,
+                                        use_gpu=True, config=make_cfg()).to(dev).eval()
+                me.use_cuda_graph = True
+                me.materialize_spatial_features = False
+                xe = synth_batch(per_gpu, 3, h, 128)[0].to(dev)
+                with torch.no_grad():
+                    for _ in range(3):
+                        me(xe)
+                    torch.cuda.synchronize()
+                    ms = _cuda_time(lambda: me(xe), 5)
+                pl = next(iter(me._plans.values()))
+                extras["eval_forward"] = {"value": per_gpu / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
+                                          "gpu_launches_per_step": sum(1 for op in pl.ops if op[0] is not None),
+                                          "what": "feature extraction (eval mode): BatchNorm / residual / ReLU in the conv epilogue"}
+                del me, xe
+            except Exception as e:
+                extras["eval_forward"] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+            try:
                 extras["eval_config5"] = eval_config5(dev, peaks)
             except Exception as e:
                 extras["eval_config5"] = {"error": repr(e)[:300]}

@@ -22,6 +22,7 @@ _SIGS = {
     "bpb_conv_num_mtiles": [_I, _I, _I],
     "bpb_conv_bn_bf16": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _I, _P, _P, _P, _P],
     "bpb_conv_bn_workspace_bytes": [_I],
+    "bpb_conv_bn_act_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "bpb_conv_ref_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "bpb_stem_conv": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bpb_stem_conv_tiles": [_I, _I, _I],

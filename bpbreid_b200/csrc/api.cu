@@ -101,6 +101,11 @@ int bpb_conv_bn_bf16(const void* x, const void* w, void* y, float* stats, int n,
     BnFuse bn{bn_workspace, gamma, beta, running_mean, running_var, scale, shift, eps, momentum, c_lo, save_mean_invstd};
     return conv_bf16_tc(x, w, y, stats, n, h, wd, cin, cout, ksize, stride, bn_hint, &bn, S(stream));
 }
+int bpb_conv_bn_act_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize,
+                         int stride, const float* scale, const float* shift, const void* res, int relu, void* stream) {
+    BnAct act{scale, shift, res, relu};
+    return conv_bf16_tc(x, w, y, nullptr, n, h, wd, cin, cout, ksize, stride, 0, nullptr, S(stream), &act);
+}
 int64_t bpb_conv_bn_workspace_bytes(int cout) { return static_cast<int64_t>(cout) * 2 * 8 + 16; }
 int bpb_conv_num_mtiles(int n, int ho, int wo) { return conv_num_mtiles(n, ho, wo); }
 int bpb_conv_ref_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize,

@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
             sc[j] = a.relu_affine ? a.scale[cv * 8 + j] : 0.f;
             sh[j] = a.relu_affine ? a.shift[cv * 8 + j] : 0.f;
         }
-#pragma unroll 2
         for (unsigned r = blockIdx.x * rows_per_block + ty; r < m; r += gridDim.x * rows_per_block) {
             float rawf[8], g[8];
             unpack8b(a.raw[static_cast<size_t>(r) * a.cvec + cv], rawf);
@@ -196,6 +195,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
     __syncthreads();
     if (s_is_last) {
         __threadfence();
+        // (measured: a block-wide tree over the partial rows, fp64 through shared memory, made this kernel 2.8x slower
+        //  than this plain per-channel loop -- profiles/launches_r2_train_step_v3.md vs _v2.md)
         for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
             double sg = 0.0, sgx = 0.0;
             for (unsigned b = 0; b < gridDim.x; ++b) {
@@ -263,7 +264,7 @@ static int bn_bwd_grid(int64_t m, int cvec) {
     return blocks;
 }
 
-constexpr int kBnRedBlocks = 148 * 4;      // reduce pass: one partial row per block, summed by the last block
+constexpr int kBnRedBlocks = 148 * 2;      // reduce pass: one partial row per block, summed by the last block
 
 int bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
                   int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,

@@ -17,8 +17,14 @@ struct BnFuse {
     int c_lo;                   // parameters cover channels [c_lo, cout) (IBN: first half is instance-normalised)
     float* save_mean_invstd;    // optional [2][cout]: batch mean and 1/sqrt(var+eps) for the backward pass
 };
+// Inference epilogue: y = act(conv * scale + shift [+ res]) written by the conv launch itself (no bn_apply pass).
+struct BnAct {
+    const float* scale; const float* shift;   // folded running statistics (bn_eval_fold)
+    const void* res;                           // optional bf16 residual shaped like y
+    int relu;
+};
 int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
-                 int ksize, int stride, int bn_hint, const BnFuse* bn, cudaStream_t stream);
+                 int ksize, int stride, int bn_hint, const BnFuse* bn, cudaStream_t stream, const BnAct* act = nullptr);
 int linear_tf32_tc(const float* a, int64_t lda, const float* w, const float* bias, float* out, int m, int n, int k,
                    int ldo, int a_mode, int a_parts, cudaStream_t stream);
 int conv_num_mtiles(int n, int ho, int wo);

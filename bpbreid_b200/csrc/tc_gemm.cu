@@ -62,9 +62,13 @@ struct GemmParams {
     float eps, momentum;
     double inv_count, unbias;
     int c_lo;
+    // EPI_BN_ACT (inference): out = act(raw * scale + shift [+ res]) written straight from the epilogue; scale / shift are
+    // INPUTS here (running statistics folded once per weight refresh), res is an optional bf16 tensor shaped like out
+    const void* res;
+    int relu;
 };
 
-enum Epi { EPI_RAW_STATS = 0, EPI_F32_BIAS = 1 };
+enum Epi { EPI_RAW_STATS = 0, EPI_F32_BIAS = 1, EPI_BN_ACT = 2 };
 
 // Persistent, warp-specialised kernel: each CTA walks output tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest so
 // consecutive tiles share their A rows in L2).  The TMA producer runs ahead across tile boundaries through the smem
@@ -92,9 +96,10 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
     const int m_tiles = p.tpg == 0 ? (p.M + kTileM - 1) / kTileM : ((p.nimg + p.bnimg - 1) / p.bnimg) * p.tpg;
     const int total_tiles = m_tiles * n_tiles;
     constexpr int kPitch = BN * 2 + 16;                        // epilogue staging tile row pitch (bytes)
-    uint8_t* epi_tile = smem + p.stages * stage_bytes;         // [128][kPitch], RAW_STATS only
+    uint8_t* epi_tile = smem + p.stages * stage_bytes;         // [128][kPitch], bf16-output epilogues only
     float* cta_stats = reinterpret_cast<float*>(epi_tile + kTileM * kPitch);   // [2][N] CTA-level column sums
     const bool fused_bn = kEpi == EPI_RAW_STATS && p.bn_acc != nullptr;
+    constexpr bool kBnAct = kEpi == EPI_BN_ACT;
     if (fused_bn)
         for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) cta_stats[i] = 0.f;
 
@@ -328,18 +333,51 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
                 {
                     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
                     constexpr int kChunksPerRow = BN / 8;
+                    // kChunksPerRow divides 128, so a thread always handles the SAME 8 channels of the tile: the folded
+                    // BatchNorm scale / shift of those channels live in registers (inference epilogue)
+                    float bsc[8], bsh[8];
+                    if constexpr (kBnAct) {
+                        const int cc0 = et % kChunksPerRow;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int chn = c_base + cc0 * 8 + j;
+                            bsc[j] = chn < p.N ? p.scale[chn] : 0.f;
+                            bsh[j] = chn < p.N ? p.shift[chn] : 0.f;
+                        }
+                    }
+                    const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(p.res);
 #pragma unroll 4
                     for (int ch = et; ch < kTileM * kChunksPerRow; ch += 128) {
                         const int r = ch / kChunksPerRow, cc = ch % kChunksPerRow;
                         if (r < valid_rows) {
-                            const uint4 o = *reinterpret_cast<const uint4*>(epi_tile + r * kPitch + cc * 16);
-                            *reinterpret_cast<uint4*>(out + static_cast<size_t>(m0 + (r >> p.chunk_log2) * p.hw + (r & cmask)) *
-                                                                p.ldo + c_base + cc * 8) = o;
+                            uint4 o = *reinterpret_cast<const uint4*>(epi_tile + r * kPitch + cc * 16);
+                            const size_t off = static_cast<size_t>(m0 + (r >> p.chunk_log2) * p.hw + (r & cmask)) * p.ldo +
+                                               c_base + cc * 8;
+                            if constexpr (kBnAct) {
+                                // BatchNorm applied to the bf16-ROUNDED conv output: bit-identical to conv -> bn_apply
+                                float f[8];
+                                f[0] = bf16_lo(o.x); f[1] = bf16_hi(o.x); f[2] = bf16_lo(o.y); f[3] = bf16_hi(o.y);
+                                f[4] = bf16_lo(o.z); f[5] = bf16_hi(o.z); f[6] = bf16_lo(o.w); f[7] = bf16_hi(o.w);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = f[j] * bsc[j] + bsh[j];
+                                if (resp != nullptr) {
+                                    const uint4 rv = *reinterpret_cast<const uint4*>(resp + off);
+                                    f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
+                                    f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+                                }
+                                if (p.relu) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                                }
+                                o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+                                o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+                            }
+                            *reinterpret_cast<uint4*>(out + off) = o;
                         }
                     }
                 }
                 // ---- per-tile column statistics from the bf16-rounded values ----
-                if (p.stats != nullptr || fused_bn) {
+                if (kEpi == EPI_RAW_STATS && (p.stats != nullptr || fused_bn)) {
                     constexpr int kPairs = BN / 2;
                     constexpr int kGroups = 128 / kPairs;                   // BN=32:8, 64:4, 128:2
                     constexpr int kRowsPer = kTileM / kGroups;              // rows each thread adds up
@@ -431,7 +469,7 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
 template <int BN, bool kTf32, int kEpi>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     const int stage_bytes = (p.a_rows + (p.mode == 3 ? 3 : 1) * BN) * p.row_bytes;
-    const size_t epi = kEpi == EPI_RAW_STATS
+    const size_t epi = kEpi != EPI_F32_BIAS
                            ? static_cast<size_t>(kTileM) * (BN * 2 + 16) + (p.bn_acc ? 2 * sizeof(float) * p.N : 0)
                            : 0;
     const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + epi + 1024;
@@ -533,8 +571,10 @@ static int pick_bn(int m_tiles, int cout, int bn_hint) {
 
 // NHWC bf16 convolution (ksize 1 or 3, stride 1 or 2, pad = ksize/2), raw bf16 output + per-tile BN partials.
 int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int h, int wd, int cin, int cout,
-                 int ksize, int stride, int bn_hint, const BnFuse* bn, cudaStream_t stream) {
+                 int ksize, int stride, int bn_hint, const BnFuse* bn, cudaStream_t stream, const BnAct* act) {
     const int pad = ksize / 2;
+    BPB_CHECK(act == nullptr || (bn == nullptr && stats == nullptr && act->scale && act->shift),
+              "conv_bf16_tc: the inference epilogue excludes the training statistics outputs");
     const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (wd + 2 * pad - ksize) / stride + 1;
     BPB_CHECK(cin % 32 == 0 && cout % 32 == 0, "conv_bf16_tc: channels must be multiples of 32 (cin=%d cout=%d)", cin,
               cout);
@@ -611,6 +651,16 @@ int conv_bf16_tc(const void* x, const void* w, void* y, float* stats, int n, int
         uint32_t box[2] = {(uint32_t)kc, (uint32_t)bn_tile};
         uint32_t es[2] = {1, 1};
         if (make_tensor_map(&tmB, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, es, sw)) return 4;
+    }
+    if (act != nullptr) {
+        p.scale = const_cast<float*>(act->scale); p.shift = const_cast<float*>(act->shift);
+        p.res = act->res; p.relu = act->relu;
+        switch (bn_tile) {
+            case 32: return launch<32, false, EPI_BN_ACT>(tmA, tmB, p, stream);
+            case 64: return launch<64, false, EPI_BN_ACT>(tmA, tmB, p, stream);
+            case 128: return launch<128, false, EPI_BN_ACT>(tmA, tmB, p, stream);
+            default: BPB_CHECK(false, "conv_bf16_tc: unsupported BN %d", bn_tile);
+        }
     }
     switch (bn_tile) {
         case 32: return launch<32, false, EPI_RAW_STATS>(tmA, tmB, p, stream);

@@ -78,6 +78,8 @@ class BPBreID(nn.Module):
         # map that is then only an *output* (5th element of the forward tuple becomes None).
         self.lowres_head = True
         self.materialize_spatial_features = True
+        # inference: BatchNorm / residual / ReLU ride the convolution's epilogue (bit-identical to conv + bn_apply)
+        self.fuse_eval_epilogue = True
 
     # -- forward ---------------------------------------------------------------------------------------------
     def _needs_masks(self):
@@ -91,7 +93,7 @@ class BPBreID(nn.Module):
         n, _, h, w = images.shape
         ext_shape = tuple(external_parts_masks.shape) if (self._needs_masks() and external_parts_masks is not None) else None
         key = (n, h, w, self.training, images.device.index, self.conv_impl, self.use_cuda_graph, self.debug_trace,
-               self.lowres_head, self.materialize_spatial_features, ext_shape)
+               self.lowres_head, self.materialize_spatial_features, ext_shape, self.fuse_eval_epilogue)
         plan = self._plans.get(key)
         if plan is None:
             from .plan import ForwardPlan

@@ -74,6 +74,7 @@ class ForwardPlan:
         self.grad = bool(grad)
         self.flat = flat
         self.tape = []
+        self.fuse_eval = getattr(model, "fuse_eval_epilogue", True)
         self.n, self.h, self.w = n, h, w
         self.training = bool(training)
         self.device = device
@@ -261,10 +262,18 @@ class ForwardPlan:
 
     def conv_bn(self, x: Act, conv, bn, c_lo=0) -> Lazy:
         """conv + BatchNorm statistics.  Training + tensor-core path: ONE launch (the conv's last CTA finalizes the
-        batch statistics into scale/shift and updates the running stats); otherwise conv, then bn_finalize / fold."""
+        batch statistics into scale/shift and updates the running stats); otherwise conv, then bn_finalize / fold.
+        Inference + tensor-core path: nothing is launched yet -- the returned Lazy is PENDING (raw is None) and the
+        consumer (`apply`, `fuse`) launches the convolution with BatchNorm / residual / ReLU in its epilogue."""
         k, s = conv.kernel_size[0], conv.stride[0]
         cout, pad = conv.out_channels, k // 2
         ho, wo = (x.h + 2 * pad - k) // s + 1, (x.w + 2 * pad - k) // s + 1
+        if (not self.training and not self.debug and c_lo == 0 and self.conv_impl == "tc" and self.fuse_eval
+                and _tc_tileable(x.c, cout, ho, wo)):
+            scale, shift = self._small((cout,)), self._small((cout,))
+            self._setup_op("bpb_bn_eval_fold", bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                           bn.running_var.data_ptr(), BN_EPS, cout, scale.data_ptr(), shift.data_ptr())
+            return Lazy(None, scale, shift, conv, x, bn, None, "pending")
         if self.training and self.conv_impl == "tc" and _tc_tileable(x.c, cout, ho, wo):
             y = self._act(x.n, ho, wo, cout)
             wp = self.pack_conv(conv)
@@ -296,8 +305,33 @@ class ForwardPlan:
                                scale[c_lo:].data_ptr(), shift[c_lo:].data_ptr())
         return Lazy(y, scale, shift)
 
+    def fused_conv(self, lz: Lazy, relu, res: Act | None = None) -> Act:
+        """launch a pending conv with BatchNorm (+ residual) (+ ReLU) in its epilogue (inference)"""
+        x, conv = lz.x_in, lz.conv
+        k, s = conv.kernel_size[0], conv.stride[0]
+        cout, pad = conv.out_channels, k // 2
+        ho, wo = (x.h + 2 * pad - k) // s + 1, (x.w + 2 * pad - k) // s + 1
+        y = self._act(x.n, ho, wo, cout)
+        self._op("bpb_conv_bn_act_bf16", x.t.data_ptr(), self.pack_conv(conv).data_ptr(), y.t.data_ptr(), x.n, x.h, x.w,
+                 x.c, cout, k, s, lz.scale.data_ptr(), lz.shift.data_ptr(), None if res is None else res.t.data_ptr(),
+                 1 if relu else 0)
+        return y
+
+    def launch_raw(self, lz: Lazy) -> Lazy:
+        """a pending conv whose consumer combines it in fp32 with other terms (projection skip, fuse-layer sum): run the
+        plain conv now (raw bf16 output), scale / shift stay with the consumer exactly like in the two-pass path"""
+        if lz.kind != "pending":
+            return lz
+        y, _, _ = self.conv_raw(lz.x_in, lz.conv, need_stats=False)
+        return Lazy(y, lz.scale, lz.shift, lz.conv, lz.x_in, lz.bn, None, "tc")
+
     def apply(self, lz: Lazy, relu, res=None) -> Act:
         """y = act(bn(raw) + res) ; res may be an Act (identity skip) or a Lazy (projection skip)."""
+        if isinstance(res, Lazy):                              # projection skip: fp32 combination in bn_apply
+            res = self.launch_raw(res)
+            lz = self.launch_raw(lz)
+        if lz.kind == "pending":
+            return self.fused_conv(lz, relu, res)
         r = lz.raw
         y = self._act(r.n, r.h, r.w, r.c)
         if res is None:
@@ -349,6 +383,7 @@ class ForwardPlan:
 
     def fuse(self, terms, out_like: Act, relu=True) -> Act:
         """terms: list of (Act | Lazy, log2 upsample factor)"""
+        terms = [(self.launch_raw(t), up) if isinstance(t, Lazy) else (t, up) for t, up in terms]
         y = self._act(out_like.n, out_like.h, out_like.w, out_like.c)
         srcs, scs, shs, ups = [], [], [], []
         for t, up in terms:

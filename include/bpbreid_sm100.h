@@ -45,6 +45,13 @@ int bpb_conv_bn_bf16(const void* x, const void* w, void* y, float* stats, int n,
                      float* shift, float* save_mean_invstd, void* stream);
 /* save_mean_invstd: optional [2][cout] fp32 -- batch mean and 1/sqrt(var + eps), kept for bpb_bn_bwd_*. */
 int64_t bpb_conv_bn_workspace_bytes(int cout);
+/* Inference: the same convolution with the (running-statistics) BatchNorm, the optional residual add and the ReLU in
+ * its epilogue: y = act(conv(x) * scale + shift [+ res]) as bf16 -- one launch instead of conv + bpb_bn_apply.
+ * scale / shift [cout] from bpb_bn_eval_fold; res NULL or a bf16 tensor shaped like y.  The BatchNorm is applied to the
+ * bf16-rounded convolution result, so the output is bit-identical to the two-launch path.
+ * Replaces conv -> bn -> (+ residual) -> relu call chains in eval mode (hrnet.py:80-96,116-137; resnet.py:128-154). */
+int bpb_conv_bn_act_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize,
+                         int stride, const float* scale, const float* shift, const void* res, int relu, void* stream);
 /* SIMT reference convolution, same operands (validation / shapes the tensor-core tiler rejects). */
 int bpb_conv_ref_bf16(const void* x, const void* w, void* y, int n, int h, int wd, int cin, int cout, int ksize,
                       int stride, void* stream);
