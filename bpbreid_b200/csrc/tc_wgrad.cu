@@ -199,10 +199,143 @@ __global__ void __launch_bounds__(256) tc_wgrad_kernel(const __grid_constant__ C
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// "Tap-stacked" variant for the row-shift layers (3x3 stride-1, chunk inside one image).
+// ncu on the kernel above (C=32 layer): tensor pipe 23 %, top stall mio_throttle -- the tensor core's own shared-memory
+// operand reads are the bound, because with Cout < 128 the M = 128 instruction re-reads the replicated dY block.  Here the
+// roles are swapped: the M side is the INPUT box, and its 128 rows are the 32|64-channel blocks of CONSECUTIVE VERTICAL
+// TAPS (descriptor LBO = Wo * row bytes: block i is the same tile entered i*Wo pixel rows further down), the N side is the
+// dY tile.  One MMA therefore produces D[(tap r, ci), co] for 4 (C=32) or 2 (C>=64) vertical taps at once: 8 instead of 24
+// (16 for C>=64) MMAs per chunk and no replicated operand reads.  Rows of a tap index >= 3 read whatever follows the box
+// in shared memory and are never written back.  Epilogue: a warp holds 32 consecutive ci of one (tap, co) per accumulator
+// column -> one coalesced 128-byte red.add per column.
+// ----------------------------------------------------------------------------------------------
+template <int NCO>
+__global__ void __launch_bounds__(224) tc_wgrad_stacked_kernel(const __grid_constant__ CUtensorMap tmY,
+                                                               const __grid_constant__ CUtensorMap tmX,
+                                                               const WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_bar[8], empty_bar[8], acc_full;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+    const int y_box_bytes = 128 * p.a_row_bytes;                       // one dY channel block
+    const int y_bytes = p.a_blocks * y_box_bytes;
+    const int x_box_bytes = (128 + 2 * p.Wo) * p.b_row_bytes;          // what the TMA box writes
+    const int stage_bytes = y_bytes + (128 + 3 * p.Wo) * p.b_row_bytes;  // + Wo slack rows under the garbage tap
+    const int cblk = p.b_row_bytes >> 1;                               // input channels per M block: 32 or 64
+    const int taps_per_acc = 128 / cblk;                               // vertical taps stacked in one accumulator
+    const int nacc = p.taps_g;                                         // accumulators == MMA warps (1 or 2)
+
+    int t = blockIdx.x;
+    const int grp = t % p.groups; t /= p.groups;                       // horizontal tap
+    const int ci_tile = t % p.ci_tiles;
+    const int co_tile = t / p.ci_tiles;
+    const int co0 = co_tile * NCO, ci0 = ci_tile * p.cit;
+    const int c_begin = static_cast<int>(static_cast<int64_t>(p.chunks) * blockIdx.y / p.ksplit);
+    const int c_end = static_cast<int>(static_cast<int64_t>(p.chunks) * (blockIdx.y + 1) / p.ksplit);
+
+    const uint32_t smem_a = smem_u32(smem);
+    const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]), accf_a = smem_u32(&acc_full);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nacc); }
+        mbar_init(&acc_full, nacc);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmX); }
+    if (warp == 1) tmem_alloc_n(&tmem_base_smem, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
+
+    if (warp == 0) {
+        const bool leader = elect_one_sync();
+        const int y_elems = p.a_row_bytes >> 1;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int c = c_begin; c < c_end; ++c) {
+            const int g = c / p.tpg;
+            const int n0 = g * p.bnimg, h0 = (c - g * p.tpg) * p.bh;
+            mbar_wait_a(empty_a + s * 8, ph ^ 1);
+            if (leader) {
+                const uint32_t dst = smem_a + s * stage_bytes, fb = full_a + s * 8;
+                mbar_expect_tx_a(fb, y_bytes + x_box_bytes);
+                for (int b = 0; b < p.a_blocks; ++b)
+                    tma_load_4d_a(dst + b * y_box_bytes, &tmY, fb, co0 + b * y_elems, 0, h0, n0);
+                tma_load_4d_a(dst + y_bytes, &tmX, fb, ci0, grp - 1, h0 - 1, n0);
+            }
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+    } else if (warp <= nacc) {
+        // M side: input box, blocks = vertical taps (LBO = Wo rows); N side: dY tile.  Both MN-major (bits 15 / 16).
+        constexpr uint32_t idesc = make_idesc(false, 128, NCO) | (1u << 15) | (1u << 16);
+        const bool leader = elect_one_sync();
+        const int g = warp - 1;
+        const uint64_t dx_hi = make_mnmajor_desc(0, p.b_row_bytes, static_cast<uint32_t>(p.Wo * p.b_row_bytes));
+        const uint64_t dy_hi = make_mnmajor_desc(0, p.a_row_bytes, p.a_blocks > 1 ? static_cast<uint32_t>(y_box_bytes) : 0u);
+        const uint32_t kstep_x = static_cast<uint32_t>(16 * p.b_row_bytes) >> 4;
+        const uint32_t kstep_y = static_cast<uint32_t>(16 * p.a_row_bytes) >> 4;
+        const uint32_t x_off = static_cast<uint32_t>(y_bytes + g * taps_per_acc * p.Wo * p.b_row_bytes);
+        const uint32_t tacc = tmem_base + g * NCO;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int c = c_begin; c < c_end; ++c) {
+            const uint32_t stage = smem_a + s * stage_bytes;
+            mbar_wait_a(full_a + s * 8, ph);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t da = dx_hi | static_cast<uint64_t>(((stage + x_off) & 0x3FFFFu) >> 4);
+                const uint64_t db = dy_hi | static_cast<uint64_t>((stage & 0x3FFFFu) >> 4);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma<false>(tacc, da + k * kstep_x, db + k * kstep_y, idesc, (c > c_begin || k > 0) ? 1u : 0u);
+                umma_commit_a(empty_a + s * 8);
+                if (c == c_end - 1) umma_commit_a(accf_a);
+            }
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+    } else if (c_end > c_begin) {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;                          // accumulator row = (vertical tap block, input channel)
+        const int bi = m / cblk, cil = m - bi * cblk;         // bi is warp-uniform (cblk >= 32)
+        mbar_wait_a(accf_a, 0);
+        tc_fence_after();
+        const int taps = 9;
+        for (int g = 0; g < nacc; ++g) {
+            const int r = g * taps_per_acc + bi;
+            const int tap = r * 3 + grp;
+#pragma unroll
+            for (int c0 = 0; c0 < NCO; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * NCO + c0, v);
+                tmem_ld_wait();
+                if (r < 3) {
+                    float* dst = p.dw + (static_cast<size_t>(co0 + c0) * taps + tap) * p.cin + ci0 + cil;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)             // lanes = 32 consecutive ci: one coalesced reduction per column
+                        atomicAdd(dst + static_cast<size_t>(j) * taps * p.cin, __uint_as_float(v[j]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_n(tmem_base, p.tmem_cols);
+    }
+}
+
 // dw [cout, ksize*ksize, cin] fp32 += wgrad(x [n,h,wd,cin] bf16, dy bf16).  dy is [n,ho,wo,cout], or with dy_up the
 // zero-inserted [n,2ho,2wo,cout].  ksize in {1,3}, stride in {1,2}, pad = ksize/2.
 int conv_wgrad_tc(const void* x, const void* dy, float* dw, int n, int h, int wd, int cin, int cout, int ksize,
                   int stride, int dy_up, cudaStream_t stream) {
+    const bool force_plain = (dy_up & 2) != 0;               // test hook: bit 1 selects the one-accumulator-per-tap kernel
+    dy_up &= 1;
     const int pad = ksize / 2;
     const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (wd + 2 * pad - ksize) / stride + 1;
     BPB_CHECK(ksize == 1 || ksize == 3, "conv_wgrad_tc: ksize %d", ksize);
@@ -264,6 +397,38 @@ int conv_wgrad_tc(const void* x, const void* dy, float* dw, int n, int h, int wd
         uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         if (make_tensor_map(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dims, strides, box, es,
                             p.b_row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return 4;
+    }
+    if (p.rowshift && !force_plain) {
+        // tap-stacked variant: accumulators = 1 (C=32: four 32-channel blocks = taps 0,1,2,x) or 2 (taps 0,1 | 2,x)
+        p.taps_g = p.b_row_bytes == 64 ? 1 : 2;
+        const int st_bytes = p.a_blocks * 128 * p.a_row_bytes + (128 + 3 * wo) * p.b_row_bytes;
+        int st = (100 * 1024) / st_bytes;
+        if (st > 6) st = 6;
+        if (st < 2) st = 2;
+        p.stages = st;
+        int tc = 32;
+        while (tc < p.taps_g * p.cot) tc <<= 1;
+        p.tmem_cols = tc;
+        const size_t sm = static_cast<size_t>(st) * st_bytes + 1024;
+        dim3 sgrid(tiles, ksplit);
+        const int threads = 32 * (5 + p.taps_g);
+        switch (p.cot) {
+            case 32:
+                BPB_SET_MAX_SMEM(tc_wgrad_stacked_kernel<32>, 200 * 1024);
+                tc_wgrad_stacked_kernel<32><<<sgrid, threads, sm, stream>>>(tmY, tmX, p);
+                break;
+            case 64:
+                BPB_SET_MAX_SMEM(tc_wgrad_stacked_kernel<64>, 200 * 1024);
+                tc_wgrad_stacked_kernel<64><<<sgrid, threads, sm, stream>>>(tmY, tmX, p);
+                break;
+            case 128:
+                BPB_SET_MAX_SMEM(tc_wgrad_stacked_kernel<128>, 200 * 1024);
+                tc_wgrad_stacked_kernel<128><<<sgrid, threads, sm, stream>>>(tmY, tmX, p);
+                break;
+            default: BPB_CHECK(false, "conv_wgrad_tc: unsupported cout tile %d", p.cot);
+        }
+        BPB_LAUNCH_CHECK("tc_wgrad_stacked_kernel");
+        return 0;
     }
     const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024;
     dim3 grid(tiles, ksplit);

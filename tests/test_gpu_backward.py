@@ -52,9 +52,11 @@ def test_conv_wgrad_tc(shape):
     ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, k, k), dy.float().permute(0, 3, 1, 2),
                                       stride=s, padding=pad)
     ref = ref.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
-    for up in ([0, 1] if s == 2 else [0]):
+    # flag bit 0: zero-inserted dY (stride-2 layers); bit 1: force the one-accumulator-per-tap kernel where the
+    # tap-stacked variant would be chosen (3x3 stride-1 row-shift layers) so that both kernels stay covered
+    for up in ([0, 1] if s == 2 else ([0, 2] if k == 3 else [0])):
         dw = torch.zeros(cout, k * k, cin, device=DEV)
-        if up:
+        if up == 1:
             dyu = torch.zeros(n, 2 * ho, 2 * wo, cout, device=DEV, dtype=torch.bfloat16)
             dyu[:, ::2, ::2] = dy
             src = dyu

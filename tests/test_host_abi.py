@@ -69,3 +69,48 @@ def test_planner_tiling_rule():
     assert not _tc_tileable(64, 64, 10, 12)          # width must divide 128
     assert _lib.query("bpb_conv_num_mtiles", 4, 24, 8) == 2 * 3 and _lib.query("bpb_conv_num_mtiles", 11, 12, 4) == 2 * 3
     assert _lib.query("bpb_conv_num_mtiles", 256, 64, 32) == 256 * 16
+
+
+def test_flat_parameter_store_keeps_state_dict_contract():
+    """bpbreid_b200.train.FlatParams re-points every nn.Parameter into one fp32 buffer: names, shapes and values of the
+    state_dict are unchanged (reference checkpoints keep loading), load_state_dict writes through into the flat buffer,
+    and the gradient buckets of the data-parallel all-reduce tile the buffer in backward order."""
+    from bpbreid_b200 import train
+    m = GI.build_product_model("hrnet32", 5, 751)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    fl = train.FlatParams(m, "cpu")
+    after = m.state_dict()
+    assert list(before) == list(after)
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+    lo, hi = fl.p.data_ptr(), fl.p.data_ptr() + 4 * fl.total
+    for name, p, off, n in fl.entries:
+        assert lo <= p.data_ptr() < hi and p.data_ptr() == lo + 4 * off and off % train.ALIGN == 0
+    sd = {k: (v + 1 if v.is_floating_point() else v) for k, v in before.items()}
+    m.load_state_dict(sd)
+    name, p, off, n = fl.entries[3]
+    assert torch.equal(fl.p[off:off + n].view(p.shape), sd[name])         # written through
+    ts = train.TrainStep(m)
+    ts.flat = fl
+
+    class FakePlan:
+        marks = [(100, "stage4"), (300, "stage3"), (500, "stage2")]
+        bops = [None] * 700
+    b = ts._buckets(FakePlan())
+    assert [x[0] for x in b] == [100, 300, 500, 700]
+    assert b[0][1][1] == fl.total and b[-1][1][0] == 0
+    assert all(b[i][1][0] == b[i + 1][1][1] for i in range(3))             # contiguous, descending
+    assert b[0][1][1] - b[0][1][0] > 0.7 * fl.total                         # head + stage 4 + incre = most parameters
+
+
+def test_extract_test_embeddings_matches_reference_semantics():
+    from bpbreid_b200 import engine
+    n, K, D = 3, 5, 8
+    g = torch.Generator().manual_seed(0)
+    emb = {"bn_foreg": torch.randn(n, D, generator=g), "parts": torch.randn(n, K, D, generator=g)}
+    vis = {"foreg": torch.rand(n, generator=g) > 0.5, "parts": torch.rand(n, K, generator=g) > 0.5}
+    masks = {"foreg": torch.rand(n, 4, 2, generator=g), "parts": torch.rand(n, K, 4, 2, generator=g)}
+    f, v, pm, pix = engine.extract_test_embeddings((emb, vis, None, "pix", None, masks), ["bn_foreg", "parts"])
+    assert f.shape == (n, K + 1, D) and v.shape == (n, K + 1) and pm.shape == (n, K + 1, 4, 2) and pix == "pix"
+    assert torch.equal(f[:, 0], emb["bn_foreg"]) and torch.equal(f[:, 1:], emb["parts"])
+    assert torch.equal(v[:, 0], vis["foreg"])                              # bn_foreg takes the visibility of foreg
