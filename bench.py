@@ -361,7 +361,7 @@ class TrainRun:
     def launches(self):
         plan = next(iter(self.ts.plans.values()))
         fwd = sum(KERNELS_PER_CALL.get(op[2], 1) for op in plan.ops if op[0] is not None)
-        return fwd + len(plan.loss_ops) + len(plan.bops) + 3
+        return fwd + len(plan.loss_ops) + sum(1 for op in plan.bops if op[0] is not None) + 3
 
 
 def timed_region(runner, args, dev, world, flush):

@@ -169,12 +169,18 @@ class ForwardPlan:
     def fork(self, lanes):
         """side lanes start after everything recorded so far on lane 0"""
         if self.multi_stream:
-            self.ops.append((None, tuple(l for l in lanes if l != 0), "fork", 0))
+            lanes = tuple(l for l in lanes if l != 0)
+            self.ops.append((None, lanes, "fork", 0))
+            self._open_lanes = lanes
+            if self.grad:
+                self.tape.append(("fork", lanes))
 
     def join(self):
         """lane 0 waits for every side lane forked since the last join"""
         if self.multi_stream:
             self.ops.append((None, (), "join", 0))
+            if self.grad:
+                self.tape.append(("join", getattr(self, "_open_lanes", ())))
 
     def _setup_op(self, name, *args):
         self.setup_ops.append((getattr(self.lib, name), args, name))
@@ -745,15 +751,20 @@ class ForwardPlan:
         if self._need_setup:
             self._run_list(self.setup_ops)
             self._need_setup = False
+        self._launch_lanes(self.ops)
+
+    def _launch_lanes(self, ops):
+        """launch a recorded op list: (fn, args, name, lane) entries on their stream lanes, (None, lanes, 'fork'|'join', 0)
+        markers as stream dependencies"""
         main = torch.cuda.current_stream()
-        nside = max((op[3] for op in self.ops), default=0)
+        nside = max((op[3] for op in ops), default=0)
         while len(self._side_streams) < nside:
             self._side_streams.append(torch.cuda.Stream(device=self.device))
         streams = [main] + self._side_streams
         ptrs = [st.cuda_stream for st in streams]
         active = []
         err = self.lib.bpb_last_error
-        for fn, args, name, lane in self.ops:
+        for fn, args, name, lane in ops:
             if fn is None:
                 if name == "fork":
                     for l in args:

@@ -147,6 +147,7 @@ class TrainPlan(ForwardPlan):
         self.btrace = []               # debug: one record per conv+BN backward (teacher-forced kernel checks in tests)
         self.head_dx = []              # debug: gradients w.r.t. the branch maps as the head backward leaves them
         self.marks = []                # (index into bops, stage name): gradient-bucket boundaries for the all-reduce
+        self._blane = 0                # stream lane the backward launches are being recorded on
         super().__init__(model, n, h, w, True, device, "tc", False, debug, grad=True, flat=flat)
 
     # ------------------------------------------------------------------ gradient bookkeeping
@@ -163,7 +164,7 @@ class TrainPlan(ForwardPlan):
 
     def galloc(self, n, h, w, c) -> Act:
         nbytes = n * h * w * c * 2
-        lst = self._gfree.get(nbytes)
+        lst = self._gfree.get((self._blane, nbytes))
         if lst:
             buf = lst.pop()
         else:
@@ -181,13 +182,15 @@ class TrainPlan(ForwardPlan):
         """return `g` to the pool if nobody else is going to read it (never in debug mode: tests inspect the buffers)"""
         if self._gref[id(g.buf)] <= 0 and not self.debug:
             self._gref[id(g.buf)] = 1 << 30                    # guards against a double free
-            self._gfree.setdefault(g.buf.numel(), []).append(g.buf)
+            # the buffer joins the pool of the lane whose launch read it LAST: the next writer is then ordered behind
+            # that reader on the same stream (the producer's lane may be running concurrently)
+            self._gfree.setdefault((self._blane, g.buf.numel()), []).append(g.buf)
 
     def _bop(self, name, *args):
-        self.bops.append((getattr(self.lib, name), args, name))
+        self.bops.append((getattr(self.lib, name), args, name, self._blane))
 
     def _bn_ws(self, c):
-        key = c
+        key = (self._blane, c)                                  # concurrent lanes must not share the partial-sum rows
         if key not in self.bwd_ws:
             self.bwd_ws[key] = torch.zeros(_lib.query("bpb_bn_bwd_workspace_bytes", c), dtype=torch.uint8,
                                            device=self.device)
@@ -274,7 +277,7 @@ class TrainPlan(ForwardPlan):
                 self.g_release(g)
             if fresh:
                 self.g_done(dy)
-        self.tape.append(bwd)
+        self.tape.append((bwd, self._lane))
         return y
 
     def fuse(self, terms, out_like: Act, relu=True) -> Act:
@@ -294,11 +297,11 @@ class TrainPlan(ForwardPlan):
             for gg in grads:
                 self.g_release(gg)
             self.g_done(g)
-        self.tape.append(bwd)
+        self.tape.append((bwd, self._lane))
         return y
 
     def mark(self, name):
-        self.tape.append(lambda: self.marks.append((len(self.bops), name)))
+        self.tape.append((lambda: self.marks.append((len(self.bops), name)), 0))
 
     def ibn_relu(self, x, conv, ibn):
         raise NotImplementedError("training backward of the IBN backbone is not built (SURVEY.md section 8 config 4)")
@@ -355,7 +358,7 @@ class TrainPlan(ForwardPlan):
                     self.head_dx.append(dx)
             if self.debug:
                 self.head_dbg = dict(dms=dms, dmts=dmts, dlows=dlows, dwf=dwf, dbf=dbf, coefab=coefab)
-        self.tape.append(bwd)
+        self.tape.append((bwd, 0))
         return ctot
 
     def build_head_front_map(self, feats):
@@ -449,13 +452,26 @@ class TrainPlan(ForwardPlan):
                           fl.grad_ptr(bn.weight), fl.grad_ptr(bn.bias))
                 self._bop("bpb_colsum_f32", dlin.data_ptr(), D, rows, D, fl.grad_ptr(fc.bias))
                 self._linear_bwd(dlin, D, rows, D, pooled2d[r0:], c, c, fc.weight, gp2d[r0:], c, fl.grad_ptr(fc.weight))
-        self.tape.append(bwd)
+        self.tape.append((bwd, 0))
 
     # ------------------------------------------------------------------ build the backward op list
     def build_backward(self):
+        """Walk the tape backwards.  Entries carry the stream lane they were recorded on in the forward pass; the
+        forward's fork / join markers turn into join / fork: the branches of an HRNet module (and its fuse outputs) are
+        independent in the backward pass exactly where they were in the forward pass."""
         assert not self._gl
-        for fn in reversed(self.tape):
+        lanes_on = self.multi_stream and not self.debug
+        for entry in reversed(self.tape):
+            if isinstance(entry[0], str):
+                kind, lanes = entry
+                if lanes_on:
+                    # reversed region: opens at the forward's join (with the lanes that region used), closes at its fork
+                    self.bops.append((None, tuple(lanes), "fork", 0) if kind == "join" else (None, (), "join", 0))
+                continue
+            fn, lane = entry
+            self._blane = lane if lanes_on else 0
             fn()
+        self._blane = 0
         self._gl.clear()
 
 
@@ -614,7 +630,7 @@ class TrainStep:
             plan.lib.bpb_memset_zero(fl.g.data_ptr(), fl.total * 4, stream)
             plan.lib.bpb_memset_zero(plan.d_emb.data_ptr(), plan.d_emb.numel() * 4, stream)
             run(plan.loss_ops)
-            run(plan.bops)
+            plan._launch_lanes(plan.bops)
             return
         for kind, fn in self._phases(plan):
             fn()
@@ -627,6 +643,9 @@ class TrainStep:
         fl = self.flat
 
         def run(ops):
+            if ops and len(ops[0]) == 4:
+                plan._launch_lanes(ops)
+                return
             stream = torch.cuda.current_stream().cuda_stream
             for fn, args, name in ops:
                 rc = fn(*args, stream)

@@ -575,3 +575,28 @@ def test_optimizer_step_moves_parameters_like_adam(trained):
     frozen = dict(m.named_parameters())["global_identity_classifier.bn.bias"]
     of = fl.off[id(frozen)]
     assert float(delta[of:of + frozen.numel()].abs().max()) == 0
+
+
+def test_multi_lane_backward_equals_single_stream():
+    """The backward pass re-uses the forward's stream lanes (HRNet branches / fuse outputs run concurrently, buffers are
+    pooled per lane): the gradients must equal those of a strictly serial recording up to the order of the fp32
+    reductions in the weight-gradient kernel."""
+    import os
+    res = []
+    for single in ("1", "0"):
+        os.environ["BPB_SINGLE_STREAM"] = single
+        try:
+            c, m, ts, plan = _train_once(8, False)
+        finally:
+            os.environ.pop("BPB_SINGLE_STREAM", None)
+        res.append((ts.flat.g.clone(), float(plan.loss_out[0]), sum(1 for op in plan.bops if op[0] is None)))
+        # a second run on the same plan must reproduce the first (pool / lane hazards would show up here)
+        g1 = ts.flat.g.clone()
+        ts.forward_backward(torch.from_numpy(c["images"]).to(DEV), torch.from_numpy(c["pids"]).to(DEV),
+                            torch.from_numpy(c["masks"]).to(DEV))
+        torch.cuda.synchronize()
+        assert rel(ts.flat.g, g1) < 1e-4
+    (g_ser, l_ser, mk_ser), (g_par, l_par, mk_par) = res
+    assert mk_ser == 0 and mk_par > 20                          # fork / join markers only in the multi-lane recording
+    assert abs(l_ser - l_par) < 1e-5 * abs(l_ser)
+    assert rel(g_par, g_ser) < 1e-4, rel(g_par, g_ser)
