@@ -579,24 +579,33 @@ def test_optimizer_step_moves_parameters_like_adam(trained):
 
 def test_multi_lane_backward_equals_single_stream():
     """The backward pass re-uses the forward's stream lanes (HRNet branches / fuse outputs run concurrently, buffers are
-    pooled per lane): the gradients must equal those of a strictly serial recording up to the order of the fp32
-    reductions in the weight-gradient kernel."""
+    pooled per lane): its gradients must agree with a strictly serial recording as well as two serial runs agree with
+    each other.  (Runs are not bit-reproducible: the head accumulates the transposed masks with shared-memory float
+    atomics and the weight gradient with global ones, and the ill-conditioned backward -- see the end-to-end test --
+    amplifies those last-bit differences.)"""
     import os
-    res = []
+    runs = {}
     for single in ("1", "0"):
         os.environ["BPB_SINGLE_STREAM"] = single
         try:
             c, m, ts, plan = _train_once(8, False)
         finally:
             os.environ.pop("BPB_SINGLE_STREAM", None)
-        res.append((ts.flat.g.clone(), float(plan.loss_out[0]), sum(1 for op in plan.bops if op[0] is None)))
-        # a second run on the same plan must reproduce the first (pool / lane hazards would show up here)
-        g1 = ts.flat.g.clone()
-        ts.forward_backward(torch.from_numpy(c["images"]).to(DEV), torch.from_numpy(c["pids"]).to(DEV),
-                            torch.from_numpy(c["masks"]).to(DEV))
-        torch.cuda.synchronize()
-        assert rel(ts.flat.g, g1) < 1e-4
-    (g_ser, l_ser, mk_ser), (g_par, l_par, mk_par) = res
+        gs = [ts.flat.g.clone()]
+        for _ in range(2):
+            ts.forward_backward(torch.from_numpy(c["images"]).to(DEV), torch.from_numpy(c["pids"]).to(DEV),
+                                torch.from_numpy(c["masks"]).to(DEV))
+            torch.cuda.synchronize()
+            gs.append(ts.flat.g.clone())
+        runs[single] = (gs, float(plan.loss_out[0]), sum(1 for op in plan.bops if op[0] is None))
+    (g_ser, l_ser, mk_ser), (g_par, l_par, mk_par) = runs["1"], runs["0"]
     assert mk_ser == 0 and mk_par > 20                          # fork / join markers only in the multi-lane recording
     assert abs(l_ser - l_par) < 1e-5 * abs(l_ser)
-    assert rel(g_par, g_ser) < 1e-4, rel(g_par, g_ser)
+    noise = max(rel(g_ser[1], g_ser[0]), rel(g_ser[2], g_ser[0]), rel(g_ser[2], g_ser[1]))
+    par_noise = max(rel(g_par[1], g_par[0]), rel(g_par[2], g_par[0]))
+    cross = max(rel(g, g_ser[0]) for g in g_par)
+    msg = f"serial run-to-run {noise:.3e}; multi-lane run-to-run {par_noise:.3e}; multi-lane vs serial {cross:.3e}"
+    print(msg)
+    os.makedirs("gpurun_out", exist_ok=True)
+    open("gpurun_out/lanes_report.txt", "w").write(msg + "\n")
+    assert cross < 3 * noise + 1e-4 and par_noise < 3 * noise + 1e-4, msg
