@@ -614,6 +614,12 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    # stdout carries exactly ONE JSON line: anything a library writes to fd 1 (NCCL prints its version banner there)
+    # goes to stderr instead, and the line is written through a private copy of the original descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
