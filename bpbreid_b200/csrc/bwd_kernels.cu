@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
     const int tx = threadIdx.x % width, ty = threadIdx.x / width;
     const unsigned m = static_cast<unsigned>(a.n) * a.h * a.w;
     const int c = a.cvec * 8;
-    __shared__ float red[2][256][8];
+    __shared__ __align__(16) float red[2][256][8];
     __shared__ int s_is_last;
     float s[8], q[8];
 #pragma unroll
@@ -141,7 +141,35 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
             sc[j] = a.relu_affine ? a.scale[cv * 8 + j] : 0.f;
             sh[j] = a.relu_affine ? a.shift[cv * 8 + j] : 0.f;
         }
-        for (unsigned r = blockIdx.x * rows_per_block + ty; r < m; r += gridDim.x * rows_per_block) {
+        const unsigned step = gridDim.x * rows_per_block;
+        unsigned r = blockIdx.x * rows_per_block + ty;
+        if (a.up_log2 == 0) {
+            // two rows per trip: four independent 16-byte loads in flight per thread (one row per trip left the pass
+            // latency-bound: 24 % active warps, long-scoreboard on top in ncu)
+            for (; r + step < m; r += 2 * step) {
+                const uint4 r0 = __ldg(a.raw + static_cast<size_t>(r) * a.cvec + cv);
+                const uint4 r1 = __ldg(a.raw + static_cast<size_t>(r + step) * a.cvec + cv);
+                const uint4 d0 = __ldg(a.dy + static_cast<size_t>(r) * a.cvec + cv);
+                const uint4 d1 = __ldg(a.dy + static_cast<size_t>(r + step) * a.cvec + cv);
+                float x0[8], x1[8], g0[8], g1[8];
+                unpack8b(r0, x0);
+                unpack8b(r1, x1);
+                unpack8b(d0, g0);
+                unpack8b(d1, g1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (a.relu_affine) {
+                        g0[j] = (x0[j] * sc[j] + sh[j]) > 0.f ? g0[j] : 0.f;
+                        g1[j] = (x1[j] * sc[j] + sh[j]) > 0.f ? g1[j] : 0.f;
+                    }
+                    s[j] += g0[j];
+                    q[j] += g0[j] * (x0[j] - mean[j]) * istd[j];
+                    s[j] += g1[j];
+                    q[j] += g1[j] * (x1[j] - mean[j]) * istd[j];
+                }
+            }
+        }
+        for (; r < m; r += step) {
             float rawf[8], g[8];
             unpack8b(a.raw[static_cast<size_t>(r) * a.cvec + cv], rawf);
             bn_bwd_load_g(a, r, cv, rawf, sc, sh, g);
@@ -195,20 +223,40 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
     __syncthreads();
     if (s_is_last) {
         __threadfence();
-        // (measured: a block-wide tree over the partial rows, fp64 through shared memory, made this kernel 2.8x slower
-        //  than this plain per-channel loop -- profiles/launches_r2_train_step_v3.md vs _v2.md)
-        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-            double sg = 0.0, sgx = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) {
-                sg += static_cast<double>(__ldcg(ws + static_cast<size_t>(b) * 2 * c + ch));
-                sgx += static_cast<double>(__ldcg(ws + static_cast<size_t>(b) * 2 * c + c + ch));
+        // the partial rows are summed by ALL threads: column (one of the 2C sums) x slice of the rows; fp64 per thread,
+        // slices combined through shared memory.  (A per-channel loop on C threads left 7/8 of the block idle for the
+        // C = 32 layers and walked up to 296 dependent L2 round trips.)
+        const int cols = 2 * c;
+        double* dred = reinterpret_cast<double*>(&red[0][0][0]);           // 2*256*8 floats = 2048 doubles
+        const int nsl = cols >= 256 ? 1 : 256 / cols;                      // row slices
+        for (int c0 = 0; c0 < cols; c0 += 256) {
+            const int col = c0 + static_cast<int>(threadIdx.x) % (cols < 256 ? cols : 256);
+            const int sl = static_cast<int>(threadIdx.x) / (cols < 256 ? cols : 256);
+            double acc0 = 0.0, acc1 = 0.0;
+            if (col < cols && sl < nsl) {
+                unsigned b = sl;
+                for (; b + nsl < gridDim.x; b += 2 * nsl) {
+                    const float v0 = __ldcg(ws + static_cast<size_t>(b) * cols + col);
+                    const float v1 = __ldcg(ws + static_cast<size_t>(b + nsl) * cols + col);
+                    acc0 += static_cast<double>(v0);
+                    acc1 += static_cast<double>(v1);
+                }
+                if (b < gridDim.x) acc0 += static_cast<double>(__ldcg(ws + static_cast<size_t>(b) * cols + col));
             }
-            coef[ch] = static_cast<float>(sg * inv_count);
-            coef[c + ch] = static_cast<float>(sgx * inv_count);
-            const int pc = ch - a.c_lo;
-            if (pc >= 0) {
-                if (dbeta) dbeta[pc] = static_cast<float>(sg);
-                if (dgamma) dgamma[pc] = static_cast<float>(sgx);
+            __syncthreads();
+            dred[threadIdx.x] = acc0 + acc1;
+            __syncthreads();
+            if (static_cast<int>(threadIdx.x) < (cols < 256 ? cols : 256) && col < cols) {
+                double t = 0.0;
+                for (int l = 0; l < nsl; ++l) t += dred[l * cols + col - c0];
+                const int ch = col < c ? col : col - c;
+                if (col < c) {
+                    coef[ch] = static_cast<float>(t * inv_count);
+                    if (dbeta && ch >= a.c_lo) dbeta[ch - a.c_lo] = static_cast<float>(t);
+                } else {
+                    coef[c + ch] = static_cast<float>(t * inv_count);
+                    if (dgamma && ch >= a.c_lo) dgamma[ch - a.c_lo] = static_cast<float>(t);
+                }
             }
         }
         if (threadIdx.x == 0) *counter = 0u;
@@ -237,7 +285,33 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a, const fl
         c2[j] = coef[c + cv * 8 + j];
     }
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-    for (unsigned r = blockIdx.x * rows_per_block + ty; r < m; r += gridDim.x * rows_per_block) {
+    const unsigned step = gridDim.x * rows_per_block;
+    unsigned r = blockIdx.x * rows_per_block + ty;
+    if (a.up_log2 == 0 && !zero_insert) {
+        for (; r + step < m; r += 2 * step) {                 // two rows per trip (four independent loads in flight)
+            const uint4 r0 = __ldg(a.raw + static_cast<size_t>(r) * a.cvec + cv);
+            const uint4 r1 = __ldg(a.raw + static_cast<size_t>(r + step) * a.cvec + cv);
+            const uint4 d0 = __ldg(a.dy + static_cast<size_t>(r) * a.cvec + cv);
+            const uint4 d1 = __ldg(a.dy + static_cast<size_t>(r + step) * a.cvec + cv);
+            float x0[8], x1[8], g0[8], g1[8], o0[8], o1[8];
+            unpack8b(r0, x0);
+            unpack8b(r1, x1);
+            unpack8b(d0, g0);
+            unpack8b(d1, g1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (a.relu_affine) {
+                    g0[j] = (x0[j] * sc[j] + sh[j]) > 0.f ? g0[j] : 0.f;
+                    g1[j] = (x1[j] * sc[j] + sh[j]) > 0.f ? g1[j] : 0.f;
+                }
+                o0[j] = k[j] * (g0[j] - c1[j] - (x0[j] - mean[j]) * istd[j] * c2[j]);
+                o1[j] = k[j] * (g1[j] - c1[j] - (x1[j] - mean[j]) * istd[j] * c2[j]);
+            }
+            out[static_cast<size_t>(r) * a.cvec + cv] = pack8b(o0);
+            out[static_cast<size_t>(r + step) * a.cvec + cv] = pack8b(o1);
+        }
+    }
+    for (; r < m; r += step) {
         float rawf[8], g[8], o[8];
         unpack8b(a.raw[static_cast<size_t>(r) * a.cvec + cv], rawf);
         bn_bwd_load_g(a, r, cv, rawf, sc, sh, g);
