@@ -92,6 +92,14 @@ struct BnBwdArgs {
     int c_lo;                   // parameters cover channels [c_lo, C)
 };
 
+// eight consecutive per-channel constants as two 16-byte loads (40 scalar loads per thread made the preamble of these
+// kernels longer than the streaming pass on the small maps)
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float* dst) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+    dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
+}
+
 __device__ __forceinline__ void bn_bwd_load_g(const BnBwdArgs& a, unsigned r, int cv, const float* rawf,
                                               const float* sc, const float* sh, float* g) {
     if (a.up_log2 == 0) {
@@ -117,55 +125,112 @@ __device__ __forceinline__ void bn_bwd_load_g(const BnBwdArgs& a, unsigned r, in
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, float* __restrict__ ws,
-                                                            unsigned int* __restrict__ counter, double inv_count,
-                                                            float* __restrict__ coef, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta) {
+// Sum `nrows` rows of `cols` floats (row stride `cols`) with all 256 threads: thread = (4-column group, row slice), up to
+// four independent 16-byte loads in flight, fp64 accumulation, slices combined through shared memory.  The column totals
+// land in dred[0 .. min(cols, 1024)) for the chunk starting at column `c0`; `emit(col, total)` is called once per column.
+template <typename Emit>
+__device__ __forceinline__ void sum_partial_rows(const float* __restrict__ base, int nrows, int cols, double* dred,
+                                                 Emit emit) {
+    const int cols4 = cols >> 2;
+    const int per = cols4 < 256 ? cols4 : 256;                     // 4-column groups handled per chunk
+    const int nsl = 256 / per;                                     // row slices
+    const int g = static_cast<int>(threadIdx.x) % per, sl = static_cast<int>(threadIdx.x) / per;
+    for (int g0 = 0; g0 < cols4; g0 += per) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (sl < nsl && g0 + g < cols4) {
+            const float4* p = reinterpret_cast<const float4*>(base) + g0 + g;
+            int r = sl;
+            for (; r + 3 * nsl < nrows; r += 4 * nsl) {
+                const float4 v0 = __ldcg(p + static_cast<size_t>(r) * cols4);
+                const float4 v1 = __ldcg(p + static_cast<size_t>(r + nsl) * cols4);
+                const float4 v2 = __ldcg(p + static_cast<size_t>(r + 2 * nsl) * cols4);
+                const float4 v3 = __ldcg(p + static_cast<size_t>(r + 3 * nsl) * cols4);
+                a0 += (static_cast<double>(v0.x) + static_cast<double>(v1.x)) + (static_cast<double>(v2.x) + static_cast<double>(v3.x));
+                a1 += (static_cast<double>(v0.y) + static_cast<double>(v1.y)) + (static_cast<double>(v2.y) + static_cast<double>(v3.y));
+                a2 += (static_cast<double>(v0.z) + static_cast<double>(v1.z)) + (static_cast<double>(v2.z) + static_cast<double>(v3.z));
+                a3 += (static_cast<double>(v0.w) + static_cast<double>(v1.w)) + (static_cast<double>(v2.w) + static_cast<double>(v3.w));
+            }
+            for (; r < nrows; r += nsl) {
+                const float4 v = __ldcg(p + static_cast<size_t>(r) * cols4);
+                a0 += static_cast<double>(v.x);
+                a1 += static_cast<double>(v.y);
+                a2 += static_cast<double>(v.z);
+                a3 += static_cast<double>(v.w);
+            }
+        }
+        __syncthreads();                                           // dred may still be read by the previous chunk
+        if (sl < nsl) {
+            double* d = dred + (static_cast<size_t>(sl) * per + g) * 4;
+            d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < per * 4; i += 256) {
+            const int col = g0 * 4 + i;
+            if (col < cols) {
+                double t = 0.0;
+                for (int l = 0; l < nsl; ++l) t += dred[static_cast<size_t>(l) * per * 4 + i];
+                emit(col, t);
+            }
+        }
+    }
+}
+
+constexpr int kBnRedBlocks = 148 * 4;      // reduce pass: one partial row per block
+constexpr int kBnRedGroup = 16;            // blocks per first-level group of the two-level deterministic row sum
+constexpr int kBnRedGroups = (kBnRedBlocks + kBnRedGroup - 1) / kBnRedGroup;
+
+// workspace: [kBnRedBlocks][2C] block rows | [kBnRedGroups][2C] group rows | kBnRedGroups + 1 counters
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdArgs a, float* __restrict__ ws, double inv_count,
+                                                               float* __restrict__ coef, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta) {
     const int width = a.cvec < 256 ? a.cvec : 256;
     const int rows_per_block = 256 / width;
     const int tx = threadIdx.x % width, ty = threadIdx.x / width;
     const unsigned m = static_cast<unsigned>(a.n) * a.h * a.w;
     const int c = a.cvec * 8;
+    const int cols = 2 * c;
     __shared__ __align__(16) float red[2][256][8];
-    __shared__ int s_is_last;
+    __shared__ int s_flag;
+    float* ws2 = ws + static_cast<size_t>(kBnRedBlocks) * cols;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws2 + static_cast<size_t>(kBnRedGroups) * cols);
+    // q accumulates g * (raw - mean); the 1/std factor is applied once per channel by the finalize
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
     const int cv = tx;
     if (ty < rows_per_block && cv < a.cvec) {
-        float mean[8], istd[8], sc[8], sh[8];
+        float mean[8], sc[8], sh[8];
+        load8f(a.mean_invstd + cv * 8, mean);
+        if (a.relu_affine) {
+            load8f(a.scale + cv * 8, sc);
+            load8f(a.shift + cv * 8, sh);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            mean[j] = a.mean_invstd[cv * 8 + j];
-            istd[j] = a.mean_invstd[c + cv * 8 + j];
-            sc[j] = a.relu_affine ? a.scale[cv * 8 + j] : 0.f;
-            sh[j] = a.relu_affine ? a.shift[cv * 8 + j] : 0.f;
+            for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sh[j] = 1.f; }     // no ReLU: gate always open
         }
         const unsigned step = gridDim.x * rows_per_block;
         unsigned r = blockIdx.x * rows_per_block + ty;
         if (a.up_log2 == 0) {
-            // two rows per trip: four independent 16-byte loads in flight per thread (one row per trip left the pass
-            // latency-bound: 24 % active warps, long-scoreboard on top in ncu)
-            for (; r + step < m; r += 2 * step) {
-                const uint4 r0 = __ldg(a.raw + static_cast<size_t>(r) * a.cvec + cv);
-                const uint4 r1 = __ldg(a.raw + static_cast<size_t>(r + step) * a.cvec + cv);
-                const uint4 d0 = __ldg(a.dy + static_cast<size_t>(r) * a.cvec + cv);
-                const uint4 d1 = __ldg(a.dy + static_cast<size_t>(r + step) * a.cvec + cv);
-                float x0[8], x1[8], g0[8], g1[8];
-                unpack8b(r0, x0);
-                unpack8b(r1, x1);
-                unpack8b(d0, g0);
-                unpack8b(d1, g1);
+            // four rows per trip: eight independent 16-byte loads in flight per thread.  (One row per trip left the
+            // pass latency-bound at ~3 TB/s: 24 % active warps, long-scoreboard on top in ncu.)
+            for (; r + 3 * step < m; r += 4 * step) {
+                uint4 xr[4], dr[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (a.relu_affine) {
-                        g0[j] = (x0[j] * sc[j] + sh[j]) > 0.f ? g0[j] : 0.f;
-                        g1[j] = (x1[j] * sc[j] + sh[j]) > 0.f ? g1[j] : 0.f;
+                for (int u = 0; u < 4; ++u) {
+                    xr[u] = __ldg(a.raw + static_cast<size_t>(r + u * step) * a.cvec + cv);
+                    dr[u] = __ldg(a.dy + static_cast<size_t>(r + u * step) * a.cvec + cv);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float x[8], g[8];
+                    unpack8b(xr[u], x);
+                    unpack8b(dr[u], g);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float gg = (x[j] * sc[j] + sh[j]) > 0.f ? g[j] : 0.f;
+                        s[j] += gg;
+                        q[j] += gg * (x[j] - mean[j]);
                     }
-                    s[j] += g0[j];
-                    q[j] += g0[j] * (x0[j] - mean[j]) * istd[j];
-                    s[j] += g1[j];
-                    q[j] += g1[j] * (x1[j] - mean[j]) * istd[j];
                 }
             }
         }
@@ -176,7 +241,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 s[j] += g[j];
-                q[j] += g[j] * (rawf[j] - mean[j]) * istd[j];
+                q[j] += g[j] * (rawf[j] - mean[j]);
             }
         }
     }
@@ -210,61 +275,55 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a, float* 
             for (int j = 0; j < 8; ++j) { s[j] += red[0][l * width + tx][j]; q[j] += red[1][l * width + tx][j]; }
         // one row of per-block partials (no atomics: ~1200 blocks adding into the same few cache lines serialised at
         // the L2 and made this kernel slower than the HBM pass it does)
-        float* mine = ws + static_cast<size_t>(blockIdx.x) * 2 * c;
+        float* mine = ws + static_cast<size_t>(blockIdx.x) * cols;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             mine[cv * 8 + j] = s[j];
             mine[c + cv * 8 + j] = q[j];
         }
     }
+    // Two-level deterministic sum of the block rows: the last block of every group of kBnRedGroup blocks folds the
+    // group's rows into one group row, the last group to finish folds the group rows and finalizes.  (One block walking
+    // all rows serially was a chain of dependent L2 round trips that outlasted the streaming pass on every map below
+    // ~30 MB: 22 us for an 8 MB map.)
+    const unsigned ngroups = (gridDim.x + kBnRedGroup - 1) / kBnRedGroup;
+    const unsigned grp = blockIdx.x / kBnRedGroup;
+    const unsigned grp_size = min(static_cast<unsigned>(kBnRedGroup), gridDim.x - grp * kBnRedGroup);
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) s_flag = atomicAdd(counters + 1 + grp, 1u) == grp_size - 1;
     __syncthreads();
-    if (s_is_last) {
-        __threadfence();
-        // the partial rows are summed by ALL threads: column (one of the 2C sums) x slice of the rows; fp64 per thread,
-        // slices combined through shared memory.  (A per-channel loop on C threads left 7/8 of the block idle for the
-        // C = 32 layers and walked up to 296 dependent L2 round trips.)
-        const int cols = 2 * c;
-        double* dred = reinterpret_cast<double*>(&red[0][0][0]);           // 2*256*8 floats = 2048 doubles
-        const int nsl = cols >= 256 ? 1 : 256 / cols;                      // row slices
-        for (int c0 = 0; c0 < cols; c0 += 256) {
-            const int col = c0 + static_cast<int>(threadIdx.x) % (cols < 256 ? cols : 256);
-            const int sl = static_cast<int>(threadIdx.x) / (cols < 256 ? cols : 256);
-            double acc0 = 0.0, acc1 = 0.0;
-            if (col < cols && sl < nsl) {
-                unsigned b = sl;
-                for (; b + nsl < gridDim.x; b += 2 * nsl) {
-                    const float v0 = __ldcg(ws + static_cast<size_t>(b) * cols + col);
-                    const float v1 = __ldcg(ws + static_cast<size_t>(b + nsl) * cols + col);
-                    acc0 += static_cast<double>(v0);
-                    acc1 += static_cast<double>(v1);
-                }
-                if (b < gridDim.x) acc0 += static_cast<double>(__ldcg(ws + static_cast<size_t>(b) * cols + col));
-            }
-            __syncthreads();
-            dred[threadIdx.x] = acc0 + acc1;
-            __syncthreads();
-            if (static_cast<int>(threadIdx.x) < (cols < 256 ? cols : 256) && col < cols) {
-                double t = 0.0;
-                for (int l = 0; l < nsl; ++l) t += dred[l * cols + col - c0];
-                const int ch = col < c ? col : col - c;
-                if (col < c) {
-                    coef[ch] = static_cast<float>(t * inv_count);
-                    if (dbeta && ch >= a.c_lo) dbeta[ch - a.c_lo] = static_cast<float>(t);
-                } else {
-                    coef[c + ch] = static_cast<float>(t * inv_count);
-                    if (dgamma && ch >= a.c_lo) dgamma[ch - a.c_lo] = static_cast<float>(t);
-                }
-            }
-        }
-        if (threadIdx.x == 0) *counter = 0u;
+    if (!s_flag) return;
+    __threadfence();
+    double* dred = reinterpret_cast<double*>(&red[0][0][0]);               // 16 KB = 2048 doubles
+    float* grow = ws2 + static_cast<size_t>(grp) * cols;
+    sum_partial_rows(ws + static_cast<size_t>(grp) * kBnRedGroup * cols, static_cast<int>(grp_size), cols, dred,
+                     [&](int col, double t) { grow[col] = static_cast<float>(t); });
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        counters[1 + grp] = 0u;
+        s_flag = atomicAdd(counters, 1u) == ngroups - 1;
     }
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    sum_partial_rows(ws2, static_cast<int>(ngroups), cols, dred, [&](int col, double t) {
+        if (col < c) {
+            coef[col] = static_cast<float>(t * inv_count);
+            if (dbeta && col >= a.c_lo) dbeta[col - a.c_lo] = static_cast<float>(t);
+        } else {
+            const int ch = col - c;
+            const double tq = t * static_cast<double>(a.mean_invstd[c + ch]);
+            coef[c + ch] = static_cast<float>(tq * inv_count);
+            if (dgamma && ch >= a.c_lo) dgamma[ch - a.c_lo] = static_cast<float>(tq);
+        }
+    });
+    if (threadIdx.x == 0) counters[0] = 0u;
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
-                                                           uint4* __restrict__ out, int zero_insert) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdArgs a, const float* __restrict__ coef,
+                                                              uint4* __restrict__ out, int zero_insert) {
     const int width = a.cvec < 256 ? a.cvec : 256;
     const int rows_per_block = 256 / width;
     const int tx = threadIdx.x % width, ty = threadIdx.x / width;
@@ -273,42 +332,47 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a, const fl
     const int c = a.cvec * 8;
     const int cv = tx;
     if (cv >= a.cvec) return;
-    float mean[8], istd[8], sc[8], sh[8], c1[8], c2[8], k[8];
+    // draw = k*(g - c1 - (raw - mean)*istd*c2) = k*g + raw*B + D  with  B = -k*c2*istd,  D = -k*c1 - mean*B
+    float sc[8], sh[8], kk[8], bb[8], dd[8];
+    {
+        float mean[8], istd[8], c1[8], c2[8];
+        load8f(a.mean_invstd + cv * 8, mean);
+        load8f(a.mean_invstd + c + cv * 8, istd);
+        load8f(a.scale + cv * 8, kk);
+        load8f(coef + cv * 8, c1);
+        load8f(coef + c + cv * 8, c2);
+        if (a.relu_affine) load8f(a.shift + cv * 8, sh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        mean[j] = a.mean_invstd[cv * 8 + j];
-        istd[j] = a.mean_invstd[c + cv * 8 + j];
-        k[j] = a.scale[cv * 8 + j];
-        sc[j] = k[j];
-        sh[j] = a.relu_affine ? a.shift[cv * 8 + j] : 0.f;
-        c1[j] = coef[cv * 8 + j];
-        c2[j] = coef[c + cv * 8 + j];
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = a.relu_affine ? kk[j] : 0.f;
+            if (!a.relu_affine) sh[j] = 1.f;                       // no ReLU: gate always open
+            bb[j] = -kk[j] * c2[j] * istd[j];
+            dd[j] = -kk[j] * c1[j] - mean[j] * bb[j];
+        }
     }
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     const unsigned step = gridDim.x * rows_per_block;
     unsigned r = blockIdx.x * rows_per_block + ty;
     if (a.up_log2 == 0 && !zero_insert) {
-        for (; r + step < m; r += 2 * step) {                 // two rows per trip (four independent loads in flight)
-            const uint4 r0 = __ldg(a.raw + static_cast<size_t>(r) * a.cvec + cv);
-            const uint4 r1 = __ldg(a.raw + static_cast<size_t>(r + step) * a.cvec + cv);
-            const uint4 d0 = __ldg(a.dy + static_cast<size_t>(r) * a.cvec + cv);
-            const uint4 d1 = __ldg(a.dy + static_cast<size_t>(r + step) * a.cvec + cv);
-            float x0[8], x1[8], g0[8], g1[8], o0[8], o1[8];
-            unpack8b(r0, x0);
-            unpack8b(r1, x1);
-            unpack8b(d0, g0);
-            unpack8b(d1, g1);
+        for (; r + 3 * step < m; r += 4 * step) {                 // four rows per trip (eight independent loads in flight)
+            uint4 xr[4], dr[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (a.relu_affine) {
-                    g0[j] = (x0[j] * sc[j] + sh[j]) > 0.f ? g0[j] : 0.f;
-                    g1[j] = (x1[j] * sc[j] + sh[j]) > 0.f ? g1[j] : 0.f;
-                }
-                o0[j] = k[j] * (g0[j] - c1[j] - (x0[j] - mean[j]) * istd[j] * c2[j]);
-                o1[j] = k[j] * (g1[j] - c1[j] - (x1[j] - mean[j]) * istd[j] * c2[j]);
+            for (int u = 0; u < 4; ++u) {
+                xr[u] = __ldg(a.raw + static_cast<size_t>(r + u * step) * a.cvec + cv);
+                dr[u] = __ldg(a.dy + static_cast<size_t>(r + u * step) * a.cvec + cv);
             }
-            out[static_cast<size_t>(r) * a.cvec + cv] = pack8b(o0);
-            out[static_cast<size_t>(r + step) * a.cvec + cv] = pack8b(o1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float x[8], g[8], o[8];
+                unpack8b(xr[u], x);
+                unpack8b(dr[u], g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float gg = (x[j] * sc[j] + sh[j]) > 0.f ? g[j] : 0.f;
+                    o[j] = kk[j] * gg + (x[j] * bb[j] + dd[j]);
+                }
+                out[static_cast<size_t>(r + u * step) * a.cvec + cv] = pack8b(o);
+            }
         }
     }
     for (; r < m; r += step) {
@@ -316,7 +380,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a, const fl
         unpack8b(a.raw[static_cast<size_t>(r) * a.cvec + cv], rawf);
         bn_bwd_load_g(a, r, cv, rawf, sc, sh, g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = k[j] * (g[j] - c1[j] - (rawf[j] - mean[j]) * istd[j] * c2[j]);
+        for (int j = 0; j < 8; ++j) o[j] = kk[j] * g[j] + (rawf[j] * bb[j] + dd[j]);
         if (!zero_insert) {
             out[static_cast<size_t>(r) * a.cvec + cv] = pack8b(o);
         } else {
@@ -333,31 +397,29 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a, const fl
 
 static int bn_bwd_grid(int64_t m, int cvec) {
     const int width = cvec < 256 ? cvec : 256;
-    int blocks = ceil_div(m, 256 / width);
+    int blocks = ceil_div(m, static_cast<int64_t>(256 / width) * 4);      // one unrolled four-row trip per thread at least
     if (blocks > 148 * 8) blocks = 148 * 8;
     return blocks;
 }
-
-constexpr int kBnRedBlocks = 148 * 2;      // reduce pass: one partial row per block, summed by the last block
 
 int bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
                   int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,
                   float* dgamma, float* dbeta, cudaStream_t stream) {
     BPB_CHECK(c % 8 == 0 && c <= 2048, "bn_bwd_reduce: C=%d must be a multiple of 8 and <= 2048", c);
     BPB_CHECK(up_log2 >= 0 && up_log2 <= 3, "bn_bwd_reduce: up_log2=%d", up_log2);
+    BPB_CHECK(((reinterpret_cast<uintptr_t>(mean_invstd) | reinterpret_cast<uintptr_t>(scale) |
+                reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
+              "bn_bwd_reduce: mean_invstd / scale / shift / workspace must be 16-byte aligned");
     BnBwdArgs a{reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(raw), mean_invstd, scale, shift,
                 n, h, w, c / 8, up_log2, relu_affine, c_lo};
-    float* ws = reinterpret_cast<float*>(workspace);
-    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + static_cast<size_t>(kBnRedBlocks) * 2 * c);
     const int64_t m = static_cast<int64_t>(n) * h * w;
-    int blocks = bn_bwd_grid(m, c / 8);
+    const int width = c / 8 < 256 ? c / 8 : 256;
+    // every thread should see at least ~4 rows (one unrolled trip), otherwise as many blocks as the row sum supports
+    int blocks = ceil_div(m, static_cast<int64_t>(256 / width) * 4);
     if (blocks > kBnRedBlocks) blocks = kBnRedBlocks;
-    // the last block walks one partial row per block: small maps get fewer, fatter blocks (>= 64 KB of `raw` each) so that
-    // this serial tail does not outlast the streaming pass (ncu: 22.9 us for a 8.4 MB map with 296 blocks)
-    const int64_t by_bytes = (m * c * 2 + 65535) / 65536;
-    if (blocks > by_bytes) blocks = static_cast<int>(by_bytes < 16 ? 16 : by_bytes);
-    if (blocks > bn_bwd_grid(m, c / 8)) blocks = bn_bwd_grid(m, c / 8);
-    bn_bwd_reduce_kernel<<<blocks, 256, 0, stream>>>(a, ws, counter, 1.0 / static_cast<double>(m), coef, dgamma, dbeta);
+    if (blocks < 1) blocks = 1;
+    bn_bwd_reduce_kernel<<<blocks, 256, 0, stream>>>(a, reinterpret_cast<float*>(workspace),
+                                                     1.0 / static_cast<double>(m), coef, dgamma, dbeta);
     BPB_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     return 0;
 }
@@ -366,6 +428,9 @@ int bn_bwd_apply(const void* dy, const void* raw, const float* mean_invstd, cons
                  const float* coef, int n, int h, int w, int c, int up_log2, int relu_affine, int zero_insert,
                  void* draw, cudaStream_t stream) {
     BPB_CHECK(c % 8 == 0 && c <= 2048, "bn_bwd_apply: C=%d must be a multiple of 8 and <= 2048", c);
+    BPB_CHECK(((reinterpret_cast<uintptr_t>(mean_invstd) | reinterpret_cast<uintptr_t>(scale) |
+                reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(coef)) & 15) == 0,
+              "bn_bwd_apply: mean_invstd / scale / shift / coef must be 16-byte aligned");
     BnBwdArgs a{reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(raw), mean_invstd, scale, shift,
                 n, h, w, c / 8, up_log2, relu_affine, 0};
     const int64_t m = static_cast<int64_t>(n) * h * w;
@@ -374,7 +439,9 @@ int bn_bwd_apply(const void* dy, const void* raw, const float* mean_invstd, cons
     return 0;
 }
 
-int64_t bn_bwd_workspace_bytes(int c) { return static_cast<int64_t>(kBnRedBlocks) * 2 * c * 4 + 16; }
+int64_t bn_bwd_workspace_bytes(int c) {
+    return (static_cast<int64_t>(kBnRedBlocks) + kBnRedGroups) * 2 * c * 4 + (kBnRedGroups + 1) * 4 + 64;
+}
 
 // ----------------------------------------------------------------------------------------------
 // Stem weight gradient (3 -> 64 channels, NCHW fp32 image, PyTorch weight layout [64][3][k][k]):

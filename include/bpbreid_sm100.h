@@ -214,7 +214,8 @@ int bpb_relu_grad_sum(const void* const* srcs, int nsrc, const void* y, void* ou
  * apply  -> draw = scale * (g - coef0 - xhat * coef1) as bf16, compact or zero-inserted (stride-2 producers).
  * g is dy, optionally gated by the following ReLU (relu_affine: raw*scale+shift > 0) and, with up_log2 > 0, summed over
  * the 2^up x 2^up block of the finer map dy lives on (adjoint of the nearest upsample of hrnet.py:239-241).
- * workspace: bpb_bn_bwd_workspace_bytes(c) bytes (per-block partial sums + a launch counter), zero-initialised once. */
+ * workspace: bpb_bn_bwd_workspace_bytes(c) bytes (per-block and per-group partial rows of a two-level deterministic sum +
+ * their counters), zero-initialised once; mean_invstd / scale / shift / coef / workspace 16-byte aligned. */
 int64_t bpb_bn_bwd_workspace_bytes(int c);
 int bpb_bn_bwd_reduce(const void* dy, const void* raw, const float* mean_invstd, const float* scale, const float* shift,
                       int n, int h, int w, int c, int up_log2, int relu_affine, int c_lo, void* workspace, float* coef,
