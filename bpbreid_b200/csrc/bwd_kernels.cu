@@ -30,28 +30,52 @@ struct GradSumArgs {
     int nsrc;
 };
 
+__device__ __forceinline__ uint4 relu_grad_sum_one(const uint4* v, int nsrc, bool gate, const uint4& yv) {
+    float acc[8];
+    unpack8b(v[0], acc);
+#pragma unroll
+    for (int s = 1; s < 4; ++s) {
+        if (s < nsrc) {
+            float f[8];
+            unpack8b(v[s], f);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[t] += f[t];
+        }
+    }
+    if (gate) {
+        float yy[8];
+        unpack8b(yv, yy);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = yy[t] > 0.f ? acc[t] : 0.f;
+    }
+    return pack8b(acc);
+}
+
 __global__ void __launch_bounds__(256) relu_grad_sum_kernel(GradSumArgs a, const uint4* __restrict__ y,
                                                             uint4* __restrict__ out, int64_t total) {
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float acc[8];
-        unpack8b(a.src[0][i], acc);
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (; i + step < total; i += 2 * step) {                 // two vectors per trip: all loads issued before any use
+        uint4 v0[4], v1[4];
 #pragma unroll
-        for (int s = 1; s < 4; ++s) {
+        for (int s = 0; s < 4; ++s) {
             if (s < a.nsrc) {
-                float f[8];
-                unpack8b(a.src[s][i], f);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) acc[t] += f[t];
+                v0[s] = __ldg(a.src[s] + i);
+                v1[s] = __ldg(a.src[s] + i + step);
             }
         }
-        if (y != nullptr) {
-            float yy[8];
-            unpack8b(y[i], yy);
+        const uint4 y0 = y ? __ldg(y + i) : zero, y1 = y ? __ldg(y + i + step) : zero;
+        out[i] = relu_grad_sum_one(v0, a.nsrc, y != nullptr, y0);
+        out[i + step] = relu_grad_sum_one(v1, a.nsrc, y != nullptr, y1);
+    }
+    for (; i < total; i += step) {
+        uint4 v0[4];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) acc[t] = yy[t] > 0.f ? acc[t] : 0.f;
-        }
-        out[i] = pack8b(acc);
+        for (int s = 0; s < 4; ++s)
+            if (s < a.nsrc) v0[s] = a.src[s][i];
+        const uint4 y0 = y ? y[i] : zero;
+        out[i] = relu_grad_sum_one(v0, a.nsrc, y != nullptr, y0);
     }
 }
 
@@ -62,7 +86,7 @@ int relu_grad_sum(const void* const* srcs, int nsrc, const void* y, void* out, i
     a.nsrc = nsrc;
     for (int s = 0; s < nsrc; ++s) a.src[s] = reinterpret_cast<const uint4*>(srcs[s]);
     const int64_t total = m * (c / 8);
-    int blocks = ceil_div(total, 256);
+    int blocks = ceil_div(total, 512);
     if (blocks > 148 * 16) blocks = 148 * 16;
     relu_grad_sum_kernel<<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const uint4*>(y), reinterpret_cast<uint4*>(out),
                                                      total);

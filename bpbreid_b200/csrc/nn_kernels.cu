@@ -315,6 +315,13 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     return o;
 }
 
+// eight consecutive per-channel constants as two 16-byte loads
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float* dst) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+    dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
+}
+
 // Thread layout: tx = channel vector (8 channels) -- fixed per thread, so scale/shift live in registers and the row
 // loop has no division; ty = row lane.  Warps read/write contiguous 16-byte vectors of consecutive rows.
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
@@ -328,14 +335,47 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
     if (ty >= rows_per_block) return;
     for (int cv = tx; cv < cvec; cv += width) {
         float sc[8], sh[8], rs[8], rb[8];
+        load8f(scale + cv * 8, sc);
+        load8f(shift + cv * 8, sh);
+        if (rscale) load8f(rscale + cv * 8, rs);
+        if (rshift) load8f(rshift + cv * 8, rb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            sc[j] = scale[cv * 8 + j];
-            sh[j] = shift[cv * 8 + j];
-            rs[j] = rscale ? rscale[cv * 8 + j] : 1.f;
-            rb[j] = rshift ? rshift[cv * 8 + j] : 0.f;
+            if (!rscale) rs[j] = 1.f;
+            if (!rshift) rb[j] = 0.f;
         }
-        for (int r = blockIdx.x * rows_per_block + ty; r < m; r += gridDim.x * rows_per_block) {
+        const int step = gridDim.x * rows_per_block;
+        int r = blockIdx.x * rows_per_block + ty;
+        // four rows per trip: up to eight independent 16-byte loads in flight per thread (one row per trip left the
+        // pass latency-bound at ~3 TB/s)
+        for (; r + 3 * step < m; r += 4 * step) {
+            uint4 xv[4], rv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const size_t i = static_cast<size_t>(r + u * step) * cvec + cv;
+                xv[u] = __ldg(x + i);
+                if (res != nullptr) rv[u] = __ldg(res + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8(xv[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
+                if (res != nullptr) {
+                    float rr[8];
+                    unpack8(rv[u], rr);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += rr[j] * rs[j] + rb[j];
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                y[static_cast<size_t>(r + u * step) * cvec + cv] = pack8(f);
+            }
+        }
+        for (; r < m; r += step) {
             const size_t i = static_cast<size_t>(r) * cvec + cv;
             float f[8];
             unpack8(x[i], f);
@@ -363,7 +403,10 @@ int bn_apply(const void* x, const float* scale, const float* shift, const void* 
     const int cvec = c / 8;
     const int width = cvec < 256 ? cvec : 256;
     const int rows_per_block = 256 / width;
-    int blocks = ceil_div(m, rows_per_block);
+    BPB_CHECK(((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift) |
+                reinterpret_cast<uintptr_t>(res_scale) | reinterpret_cast<uintptr_t>(res_shift)) & 15) == 0,
+              "bn_apply: scale / shift vectors must be 16-byte aligned");
+    int blocks = ceil_div(m, static_cast<int64_t>(rows_per_block) * 4);   // one unrolled four-row trip per thread at least
     if (blocks > 148 * 8) blocks = 148 * 8;
     bn_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), scale, shift,
                                                 reinterpret_cast<const uint4*>(res), res_scale, res_shift,
