@@ -60,6 +60,15 @@ _SIGS = {
     "bpb_l2_normalize": [_P, _P, _L, _I, _F, _P],
     "bpb_resize_bilinear_f32": [_P, _P, _L, _I, _I, _I, _I, _P],
     "bpb_conv_wgrad_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "bpb_rerank_build": [_P, _P, _P, _I, _I, _P, _P, _P],
+    "bpb_rerank_topk": [_P, _I, _I, _P, _P],
+    "bpb_rerank_row_capacity": [_I],
+    "bpb_rerank_kreciprocal": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "bpb_rerank_qexpand": [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "bpb_rerank_csc_count": [_P, _P, _I, _I, _P, _P],
+    "bpb_rerank_csc_fill": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "bpb_rerank_jaccard_blocks": [_I, _I],
+    "bpb_rerank_jaccard": [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P],
     "bpb_relu_grad_sum": [_P, _I, _P, _P, _L, _I, _P],
     "bpb_bn_bwd_workspace_bytes": [_I],
     "bpb_bn_bwd_reduce": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],

@@ -349,4 +349,37 @@ int bpb_l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, v
     return l2_normalize(x, y, rows, d, eps, S(stream));
 }
 
+
+/* ---- k-reciprocal re-ranking ---- */
+int bpb_rerank_build(const float* qg, const float* qq, const float* gg, int nq, int ng, float* colmax, float* orig,
+                     void* stream) {
+    return rerank_build(qg, qq, gg, nq, ng, colmax, orig, S(stream));
+}
+int bpb_rerank_topk(const float* orig, int a, int k, int32_t* rank, void* stream) {
+    return rerank_topk(orig, a, k, rank, S(stream));
+}
+int bpb_rerank_row_capacity(int k1) { return rerank_row_capacity(k1); }
+int bpb_rerank_kreciprocal(const float* orig, const int32_t* rank, int a, int rank_cols, int k1, int32_t* vidx, float* vval,
+                           int32_t* vcnt, void* stream) {
+    return rerank_kreciprocal(orig, rank, a, rank_cols, k1, vidx, vval, vcnt, S(stream));
+}
+int bpb_rerank_qexpand(const int32_t* rank, int rank_cols, int k2, const int32_t* vidx, const float* vval,
+                       const int32_t* vcnt, int k1, int a, int32_t* qidx, float* qval, int32_t* qcnt, void* stream) {
+    return rerank_qexpand(rank, rank_cols, k2, vidx, vval, vcnt, k1, a, qidx, qval, qcnt, S(stream));
+}
+int bpb_rerank_csc_count(const int32_t* qidx, const int32_t* qcnt, int qcap, int a, int32_t* colcnt, void* stream) {
+    return rerank_csc_count(qidx, qcnt, qcap, a, colcnt, S(stream));
+}
+int bpb_rerank_csc_fill(const int32_t* qidx, const float* qval, const int32_t* qcnt, int qcap, int a,
+                        const int32_t* col_ptr, int32_t* cursor, int32_t* crow, float* cval, void* stream) {
+    return rerank_csc_fill(qidx, qval, qcnt, qcap, a, col_ptr, cursor, crow, cval, S(stream));
+}
+int bpb_rerank_jaccard_blocks(int nq, int a) { return rerank_jaccard_blocks(nq, a); }
+int bpb_rerank_jaccard(const float* orig, const int32_t* qidx, const float* qval, const int32_t* qcnt, int qcap,
+                       const int32_t* col_ptr, const int32_t* crow, const float* cval, int nq, int a,
+                       float one_minus_lambda, float lambda, float* scratch, float* out, void* stream) {
+    return rerank_jaccard(orig, qidx, qval, qcnt, qcap, col_ptr, crow, cval, nq, a, one_minus_lambda, lambda, scratch, out,
+                          S(stream));
+}
+
 }  // extern "C"

@@ -172,6 +172,23 @@ int head_branch_bwd(const void* x, const float* mt, const float* gs, const float
 
 // ---- eval_kernels.cu --------------------------------------------------------------------------
 int l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, cudaStream_t stream);
+
+// k-reciprocal re-ranking (rerank.cu)
+int rerank_build(const float* qg, const float* qq, const float* gg, int nq, int ng, float* cmax, float* orig,
+                 cudaStream_t stream);
+int rerank_topk(const float* orig, int a, int k, int* rank, cudaStream_t stream);
+int rerank_row_capacity(int k1);
+int rerank_kreciprocal(const float* orig, const int* rank, int a, int rk, int k1, int* vidx, float* vval, int* vcnt,
+                       cudaStream_t stream);
+int rerank_qexpand(const int* rank, int rk, int k2, const int* vidx, const float* vval, const int* vcnt, int k1, int a,
+                   int* qidx, float* qval, int* qcnt, cudaStream_t stream);
+int rerank_csc_count(const int* qidx, const int* qcnt, int qcap, int a, int* colcnt, cudaStream_t stream);
+int rerank_csc_fill(const int* qidx, const float* qval, const int* qcnt, int qcap, int a, const int* col_ptr, int* cursor,
+                    int* crow, float* cval, cudaStream_t stream);
+int rerank_jaccard_blocks(int nq, int a);
+int rerank_jaccard(const float* orig, const int* qidx, const float* qval, const int* qcnt, int qcap, const int* col_ptr,
+                   const int* crow, const float* cval, int nq, int a, float one_minus_lambda, float lambda, float* scratch,
+                   float* out, cudaStream_t stream);
 int resize_bilinear_f32(const float* in, float* out, int64_t planes, int hi, int wi, int ho, int wo, cudaStream_t stream);
 
 }  // namespace bpb

@@ -117,13 +117,34 @@ class ImagePartBasedEngine:
             qf, gf = self.normalize(qf), self.normalize(gf)
         impl = 1 if exact_distance else 0
         dist, part = metrics.part_distance_device(qf, gf, qv, gv, self.dist_combine_strat, dist_metric, impl=impl)
-        if rerank:
-            raise NotImplementedError("k-reciprocal re-ranking (torchreid/utils/rerank.py:31-113, off by default: "
-                                      "test.rerank False) is outside the hot path built here (SURVEY.md section 8 f3)")
+        if rerank:                                                   # part_based_engine.py:218-226
+            from .rerank import re_ranking_device
+            qq, _ = metrics.part_distance_device(qf, qf, qv, qv, self.dist_combine_strat, dist_metric, impl=impl,
+                                                 want_part_dist=False)
+            gg, _ = metrics.part_distance_device(gf, gf, gv, gv, self.dist_combine_strat, dist_metric, impl=impl,
+                                                 want_part_dist=False)
+            dist = re_ranking_device(dist, qq, gg)
         res = metrics.rank_device(dist, q_pids, g_pids, q_camids, g_camids, max_rank)
         metrics._check_rank(res, dist.shape[1], max_rank)
         self.last_distmat, self.last_body_parts_distmat = dist, part
         return res["cmc"].cpu().numpy(), float(res["mAP"].item())
+
+    def individual_parts_ranking_performances(self, body_parts_distmat, q_pids, g_pids, q_camids, g_camids, max_rank=50):
+        """display_individual_parts_ranking_performances (part_based_engine.py:308-339) without the printing: one
+        device-resident CMC/mAP evaluation per test embedding; returns rows [title, mAP, R-1, R-5, R-10]."""
+        emb = self.test_embeddings
+        offset = int("globl" in emb) + int("foreg" in emb)
+        table = []
+        for bp in range(body_parts_distmat.shape[0]):
+            res = metrics.rank_device(body_parts_distmat[bp], q_pids, g_pids, q_camids, g_camids, max_rank)
+            metrics._check_rank(res, body_parts_distmat.shape[2], max_rank)
+            cmc = res["cmc"].cpu().numpy()
+            title = "p {}".format(bp - offset)
+            if bp < offset:
+                title = ("globl" if "globl" in emb else "foreg") if bp == 0 else "foreg"
+            table.append([title, float(res["mAP"].item()), float(cmc[0]), float(cmc[min(4, len(cmc) - 1)]),
+                          float(cmc[min(9, len(cmc) - 1)])])
+        return table
 
     # ------------------------------------------------------------------ training
     def combine_losses(self, visibility_scores_dict, embeddings_dict, id_cls_scores_dict, pids, pixels_cls_scores=None,

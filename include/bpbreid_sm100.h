@@ -294,6 +294,35 @@ int bpb_resize_bilinear_f32(const float* in, float* out, int64_t planes, int hi,
  * [N, P, D] test embeddings at torchreid/engine/image/part_based_engine.py:205-208. */
 int bpb_l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, void* stream);
 
+/* ---- k-reciprocal re-ranking: torchreid/utils/rerank.py:31-113, called at part_based_engine.py:218-226 -------------
+ * Stages of one re_ranking(q_g, q_q, g_g, k1, k2, lambda) call, all device-resident (A = nq + ng):
+ *  build       orig[A][A] = transpose(D^2 / colmax(D^2)), D = [[qq, qg], [qg^T, gg]]   (rerank.py:36-46); colmax: A floats
+ *  topk        rank[A][k] = first k columns of the stable argsort of every row of orig  (rerank.py:47; the reference's
+ *              introsort may permute exact ties, this is the (value, index) order)
+ *  kreciprocal expanded k-reciprocal sets + weights exp(-orig)/sum as sparse rows of capacity
+ *              bpb_rerank_row_capacity(k1): vidx/vval [A][cap], vcnt [A]               (rerank.py:54-79); k1 <= 31
+ *  qexpand     local query expansion: mean of the rows V[rank[i, :k2]] as sorted sparse rows of capacity
+ *              min(k2, A)*cap: qidx/qval/qcnt (k2 == 1: rows copied and sorted)         (rerank.py:81-86); k2*cap <= 4096
+ *  csc_count / csc_fill   column-compressed copy (rerank.py:88-90): colcnt[A]; the caller turns it into the exclusive
+ *              prefix col_ptr[A+1]; cursor[A] scratch; crow/cval sized col_ptr[A]
+ *  jaccard     out[nq][ng] = (1 - t/(2-t))*(1-lambda) + orig[:nq, nq:]*lambda, t = sum_c min(V[i,c], V[g,c])
+ *              (rerank.py:92-111); scratch: bpb_rerank_jaccard_blocks(nq, A)*A floats, only read when A*4 > 200 KB */
+int bpb_rerank_build(const float* qg, const float* qq, const float* gg, int nq, int ng, float* colmax, float* orig,
+                     void* stream);
+int bpb_rerank_topk(const float* orig, int a, int k, int32_t* rank, void* stream);
+int bpb_rerank_row_capacity(int k1);
+int bpb_rerank_kreciprocal(const float* orig, const int32_t* rank, int a, int rank_cols, int k1, int32_t* vidx, float* vval,
+                           int32_t* vcnt, void* stream);
+int bpb_rerank_qexpand(const int32_t* rank, int rank_cols, int k2, const int32_t* vidx, const float* vval,
+                       const int32_t* vcnt, int k1, int a, int32_t* qidx, float* qval, int32_t* qcnt, void* stream);
+int bpb_rerank_csc_count(const int32_t* qidx, const int32_t* qcnt, int qcap, int a, int32_t* colcnt, void* stream);
+int bpb_rerank_csc_fill(const int32_t* qidx, const float* qval, const int32_t* qcnt, int qcap, int a,
+                        const int32_t* col_ptr, int32_t* cursor, int32_t* crow, float* cval, void* stream);
+int bpb_rerank_jaccard_blocks(int nq, int a);
+int bpb_rerank_jaccard(const float* orig, const int32_t* qidx, const float* qval, const int32_t* qcnt, int qcap,
+                       const int32_t* col_ptr, const int32_t* crow, const float* cval, int nq, int a,
+                       float one_minus_lambda, float lambda, float* scratch, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

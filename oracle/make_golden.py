@@ -114,6 +114,23 @@ def gen_rank(ref):
     print("rank.npz", len(out))
 
 
+def gen_rerank():
+    """tests/golden/rerank.npz: the UNMODIFIED reference re-ranking (torchreid/utils/rerank.py, numpy only, imported by
+    path from where it lies) on the seeded cases of tests/golden_inputs.py::rerank_case."""
+    import importlib.util
+    from tests.golden_inputs import RERANK_CASES, rerank_case
+    spec = importlib.util.spec_from_file_location("ref_rerank", os.path.join(ref_loader.REF_PKG, "utils", "rerank.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {}
+    for name in RERANK_CASES:
+        c = rerank_case(name)
+        out[f"{name}/final"] = mod.re_ranking(c["q_g"], c["q_q"], c["g_g"], k1=c["k1"], k2=c["k2"],
+                                              lambda_value=c["lam"]).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "rerank.npz"), **out)
+    print("rerank.npz", len(out))
+
+
 def gen_models(ref, only=None):
     for name in (only or MODEL_CASES):
         c = model_case(name)
@@ -210,13 +227,15 @@ def gen_grads(ref, name="hrnet32_k5_ctr", bpa_weight=0.35):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
-    which = sys.argv[1:] or ["losses", "distance", "rank", "models", "grads", "masks"]
+    which = sys.argv[1:] or ["losses", "distance", "rank", "rerank", "models", "grads", "masks"]
     if "losses" in which:
         gen_losses(ref)
     if "distance" in which:
         gen_distance(ref)
     if "rank" in which:
         gen_rank(ref)
+    if "rerank" in which:
+        gen_rerank()
     if "models" in which:
         gen_models(ref)
     only = [w.split(":", 1)[1] for w in which if w.startswith("models:")]

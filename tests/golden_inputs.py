@@ -112,6 +112,31 @@ def rank_case(name):
                 q_camids=q_cam.astype(np.int64), g_camids=g_cam.astype(np.int64), max_rank=max_rank)
 
 
+# k-reciprocal re-ranking (utils/rerank.py:31-113): name -> (Nq, Ng, identities, k1, k2, lambda)
+RERANK_CASES = {"clusters": (40, 160, 20, 20, 6, 0.3),        # the engine's defaults (part_based_engine.py:226)
+                "small_k": (24, 100, 12, 5, 1, 0.5),           # k1/2 = 2.5 rounds to even, k2 == 1 skips the expansion
+                "tiny": (6, 14, 4, 20, 6, 0.3)}                # k1 + 1 > Nq + Ng: every neighbour list is truncated
+
+
+def rerank_case(name):
+    """Euclidean distance matrices between L2-normalised clustered features (float32, no exact ties off the diagonal)."""
+    nq, ng, nid, k1, k2, lam = RERANK_CASES[name]
+    rs = np.random.RandomState(list(RERANK_CASES).index(name) + 71)
+    centres = rs.randn(nid, 48).astype(F32)
+
+    def feats(n):
+        ids = rs.randint(0, nid, n)
+        f = centres[ids] + 0.6 * rs.randn(n, 48).astype(F32)
+        return (f / np.linalg.norm(f, axis=1, keepdims=True)).astype(F32), ids
+
+    def dist(a, b):
+        d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * (a @ b.T)
+        return np.sqrt(np.maximum(d2, 0)).astype(F32)
+
+    (qf, qid), (gf, gid) = feats(nq), feats(ng)
+    return dict(q_g=dist(qf, gf), q_q=dist(qf, qf), g_g=dist(gf, gf), k1=k1, k2=k2, lam=lam, q_pids=qid, g_pids=gid)
+
+
 MODEL_CASES = ["hrnet32_k5", "resnet50_k5", "ibn_k8", "hrnet32_k5_384", "hrnet32_k5_ctr"]
 # external part masks (bpbreid.py:149-175): name -> (base case, config overrides); eval-mode goldens with the masks passed
 MASK_CASES = {"hrnet32_k5_extattn": ("hrnet32_k5", dict(learnable_attention_enabled=False)),

@@ -139,3 +139,12 @@ def test_oracle_autograd_matches_reference_backward(golden):
             continue
         err = np.abs(grads[k].numpy() - ref).max() / (np.abs(ref).max() + 1e-12)
         assert err < 2e-2, (k, err)
+
+
+@pytest.mark.parametrize("name", list(GI.RERANK_CASES))
+def test_rerank_oracle_reproduces_reference_bit_for_bit(golden, name):
+    """oracle/rerank_oracle.py vs the unmodified torchreid/utils/rerank.py output stored in tests/golden/rerank.npz."""
+    from oracle import rerank_oracle as RO
+    c = GI.rerank_case(name)
+    out = RO.re_ranking(c["q_g"], c["q_q"], c["g_g"], c["k1"], c["k2"], c["lam"])
+    np.testing.assert_array_equal(out, golden("rerank")[f"{name}/final"])
