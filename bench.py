@@ -271,7 +271,23 @@ def eval_config5(dev, peaks, nq=4096, ng=16384, p=6, d=512, reps=5):
     torch.cuda.synchronize()
     r_ms = float(np.median([_cuda_time(run_rank, 1) for _ in range(reps)]))
     algo = (nq + ng) * p * d * 4 + nq * ng * 4 * (p + 1)
-    return {"workload": f"part distance {nq}x{ng}, P={p}, D={d}, bool visibility, mean + market1501 CMC/mAP",
+    # optional k-reciprocal re-ranking (part_based_engine.py:218-226): q-q and g-g distances + rerank.py on the device
+    rr = None
+    try:
+        from bpbreid_b200 import rerank
+
+        def run_rerank():
+            qq, _ = metrics.part_distance_device(qf, qf, qv, qv, "mean", "euclidean", 0, False)
+            gg, _ = metrics.part_distance_device(gf, gf, gv, gv, "mean", "euclidean", 0, False)
+            return rerank.re_ranking_device(dist, qq, gg)
+        run_rerank()
+        torch.cuda.synchronize()
+        rr = {"ms": float(np.median([_cuda_time(run_rerank, 1) for _ in range(3)])),
+              "what": "q-q + g-g part distances and k-reciprocal re-ranking (k1=20, k2=6), device-resident"}
+    except Exception as e:
+        rr = {"error": repr(e)[:200]}
+    torch.cuda.empty_cache()
+    return {"rerank": rr, "workload": f"part distance {nq}x{ng}, P={p}, D={d}, bool visibility, mean + market1501 CMC/mAP",
             "distance_ms": d_ms, "rank_ms": r_ms, "mAP": float(res["mAP"].item()),
             "roofline": {"bound": "hbm", "kernel": "part_distance_tc_kernel (+ norms, masks, fix-up)",
                          "algorithmic_bytes": algo, "achieved": algo / (d_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
