@@ -60,6 +60,8 @@ _SIGS = {
     "bpb_l2_normalize": [_P, _P, _L, _I, _F, _P],
     "bpb_resize_bilinear_f32": [_P, _P, _L, _I, _I, _I, _I, _P],
     "bpb_conv_wgrad_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "bpb_preprocess_images": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "bpb_preprocess_masks": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _F, _F, _P, _P],
     "bpb_rerank_build": [_P, _P, _P, _I, _I, _P, _P, _P],
     "bpb_rerank_topk": [_P, _I, _I, _P, _P],
     "bpb_rerank_row_capacity": [_I],

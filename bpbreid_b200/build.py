@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbpbreid_sm100.so")
-SOURCES = ["api.cu", "tc_gemm.cu", "nn_kernels.cu", "head.cu", "head_lowres.cu", "loss.cu", "distance.cu", "rank.cu", "eval_kernels.cu", "tc_wgrad.cu", "bwd_kernels.cu", "loss_bwd.cu", "head_bwd.cu", "rerank.cu"]
+SOURCES = ["api.cu", "tc_gemm.cu", "nn_kernels.cu", "head.cu", "head_lowres.cu", "loss.cu", "distance.cu", "rank.cu", "eval_kernels.cu", "tc_wgrad.cu", "bwd_kernels.cu", "loss_bwd.cu", "head_bwd.cu", "rerank.cu", "input_pipeline.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

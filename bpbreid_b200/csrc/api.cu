@@ -350,6 +350,19 @@ int bpb_l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, v
 }
 
 
+/* ---- input pipeline ---- */
+int bpb_preprocess_images(const uint8_t* pixels, const int64_t* offsets, const int32_t* geom, int n, int height, int width,
+                          int pad, const float* mean255, const float* inv_std255, const float* erase_fill, float* out,
+                          void* stream) {
+    return preprocess_images(pixels, offsets, geom, n, height, width, pad, mean255, inv_std255, erase_fill, out, S(stream));
+}
+int bpb_preprocess_masks(const float* fields, const int64_t* offsets, const int32_t* geom, int n, int height, int width,
+                         int out_h, int out_w, int pad, const uint64_t* group_bits, int parts, int combine_sum,
+                         int strategy, float threshold, float softmax_weight, float* out, void* stream) {
+    return preprocess_masks(fields, offsets, geom, n, height, width, out_h, out_w, pad, group_bits, parts, combine_sum,
+                            strategy, threshold, softmax_weight, out, S(stream));
+}
+
 /* ---- k-reciprocal re-ranking ---- */
 int bpb_rerank_build(const float* qg, const float* qq, const float* gg, int nq, int ng, float* colmax, float* orig,
                      void* stream) {

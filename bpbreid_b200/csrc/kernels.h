@@ -173,6 +173,14 @@ int head_branch_bwd(const void* x, const float* mt, const float* gs, const float
 // ---- eval_kernels.cu --------------------------------------------------------------------------
 int l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, cudaStream_t stream);
 
+// input pipeline (input_pipeline.cu); mean255 / inv_std255 / erase_fill / group_bits are HOST arrays
+int preprocess_images(const uint8_t* pixels, const int64_t* offsets, const int32_t* geom, int n, int height, int width,
+                      int pad, const float* mean255, const float* inv_std255, const float* erase_fill, float* out,
+                      cudaStream_t stream);
+int preprocess_masks(const float* fields, const int64_t* offsets, const int32_t* geom, int n, int height, int width,
+                     int out_h, int out_w, int pad, const uint64_t* group_bits, int parts, int combine_sum, int strategy,
+                     float threshold, float softmax_weight, float* out, cudaStream_t stream);
+
 // k-reciprocal re-ranking (rerank.cu)
 int rerank_build(const float* qg, const float* qq, const float* gg, int nq, int ng, float* cmax, float* orig,
                  cudaStream_t stream);

@@ -294,6 +294,24 @@ int bpb_resize_bilinear_f32(const float* in, float* out, int64_t planes, int hi,
  * [N, P, D] test embeddings at torchreid/engine/image/part_based_engine.py:205-208. */
 int bpb_l2_normalize(const float* x, float* y, int64_t rows, int d, float eps, void* stream);
 
+/* ---- input pipeline: torchreid/data/transforms.py:73-163 (build_transforms' per-sample list) and
+ * torchreid/data/masks_transforms/mask_transform.py:21-85, one launch per batch -------------------------------------
+ * Every sample has its own source size: `offsets[n]` (elements from the base pointer) and `geom[n][10]` =
+ * {src_h, src_w, flip, crop_x, crop_y (-1: no crop), erase_x0, erase_y0, erase_x1, erase_y1, 0}; the host draws the
+ * augmentation parameters.  mean255 / inv_std255 / erase_fill / group_bits are HOST arrays (copied into the launch).
+ *  images: RGB uint8 HWC -> cv2.resize(INTER_LINEAR) fixed-point, bit-exact -> flip -> zero pad `pad` + crop ->
+ *          (x - mean255) * inv_std255 (albumentations.Normalize) -> erase rectangle := erase_fill -> out [n][3][H][W] f32
+ *  masks:  fields float [36][src_h][src_w] per sample -> cv2 INTER_NEAREST to (H, W) -> flip / pad+crop / erase with 0 ->
+ *          parts = clamp(max|sum over group_bits[k]) (MaskGroupingTransform) -> background (strategy 0 sum,
+ *          1 threshold, 2 diff_from_max; AddBackgroundMask) -> softmax(weight*m) (weight <= 0: m / sum) ->
+ *          nearest resize to (out_h, out_w) (ResizeMasks) -> out [n][parts+1][out_h][out_w] f32 */
+int bpb_preprocess_images(const uint8_t* pixels, const int64_t* offsets, const int32_t* geom, int n, int height, int width,
+                          int pad, const float* mean255, const float* inv_std255, const float* erase_fill, float* out,
+                          void* stream);
+int bpb_preprocess_masks(const float* fields, const int64_t* offsets, const int32_t* geom, int n, int height, int width,
+                         int out_h, int out_w, int pad, const uint64_t* group_bits, int parts, int combine_sum,
+                         int strategy, float threshold, float softmax_weight, float* out, void* stream);
+
 /* ---- k-reciprocal re-ranking: torchreid/utils/rerank.py:31-113, called at part_based_engine.py:218-226 -------------
  * Stages of one re_ranking(q_g, q_q, g_g, k1, k2, lambda) call, all device-resident (A = nq + ng):
  *  build       orig[A][A] = transpose(D^2 / colmax(D^2)), D = [[qq, qg], [qg^T, gg]]   (rerank.py:36-46); colmax: A floats

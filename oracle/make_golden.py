@@ -131,6 +131,75 @@ def gen_rerank():
     print("rerank.npz", len(out))
 
 
+def gen_inputs():
+    """tests/golden/inputs.npz: the reference's mask transforms (mask_transform.py / pifpaf_mask_transform.py, imported
+    from where they lie with a stub for the absent albumentations base class) composed in build_transforms' order
+    (transforms.py:73-163) with cv2.resize doing what albumentations.Resize does; images: cv2.resize + the restated
+    albumentations.Normalize.  Also stores the reference's group tables so the product's restated tables are checked."""
+    import importlib
+    import types
+
+    import cv2
+    from oracle import input_oracle as IO
+    from tests.golden_inputs import INPUT_CASES, input_case
+    alb = types.ModuleType("albumentations")
+
+    class DualTransform:                                        # the only albumentations name mask_transform.py uses
+        def __init__(self, always_apply=False, p=0.5):
+            pass
+    alb.DualTransform = DualTransform
+    sys.modules["albumentations"] = alb
+    for name, sub in (("torchreid.data", "data"), ("torchreid.data.masks_transforms", "data/masks_transforms")):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(ref_loader.REF_PKG, sub)]
+        m.__package__ = name
+        sys.modules[name] = m
+    mt = importlib.import_module("torchreid.data.masks_transforms.mask_transform")
+    pp = importlib.import_module("torchreid.data.masks_transforms.pifpaf_mask_transform")
+    classes = {"five_v": pp.CombinePifPafIntoFiveVerticalParts, "eight": pp.CombinePifPafIntoEightBodyMasks}
+    out = {}
+    for prep, cls in classes.items():
+        t = cls()
+        tab = np.zeros((t.parts_num, 36), np.uint8)
+        for i, part in enumerate(t.parts_names):
+            for k in t.parts_grouping[part]:
+                tab[i, t.parts_map[k]] = 1
+        out[f"groups/{prep}"] = tab
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    for name in INPUT_CASES:
+        c = input_case(name)
+        h, w = c["height"], c["width"]
+        group = classes[c["preprocess"]]()
+        addbg = mt.AddBackgroundMask(c["strategy"], c["softmax_weight"], c["threshold"])
+        resize = mt.ResizeMasks(h, w, 4)
+        imgs, masks = [], []
+        for img, f, p in zip(c["images"], c["fields"], c["params"]):
+            x = cv2.resize(img, (w, h), interpolation=cv2.INTER_LINEAR)
+            m = np.transpose(f, (1, 2, 0))                                  # read_masks: HWC (utils/tools.py:139-140)
+            m = np.stack([cv2.resize(np.ascontiguousarray(m[:, :, k]), (w, h), interpolation=cv2.INTER_NEAREST)
+                          for k in range(36)], axis=2)
+            if p["flip"]:
+                x, m = np.ascontiguousarray(x[:, ::-1]), np.ascontiguousarray(m[:, ::-1])
+            if p["crop"] is not None:
+                x = cv2.copyMakeBorder(x, 10, 10, 10, 10, cv2.BORDER_CONSTANT, value=0)
+                m = np.pad(m, ((10, 10), (10, 10), (0, 0)))
+                cx, cy = p["crop"]
+                x, m = x[cy:cy + h, cx:cx + w], m[cy:cy + h, cx:cx + w]
+            xf = IO.normalize(np.ascontiguousarray(x), mean, std)
+            if p["erase"] is not None:
+                x0, y0, x1, y1 = p["erase"]
+                xf[y0:y1, x0:x1] = np.array([0.485, 0.456, 0.406], np.float32)
+                m = m.copy()
+                m[y0:y1, x0:x1] = 0
+            imgs.append(xf.transpose(2, 0, 1))
+            t = mt.PermuteMasksDim().apply_to_mask(torch.as_tensor(np.ascontiguousarray(m)))
+            t = resize.apply_to_mask(addbg.apply_to_mask(group.apply_to_mask(t)))
+            masks.append(t.numpy())
+        out[f"{name}/images"], out[f"{name}/masks"] = np.stack(imgs).astype(np.float32), np.stack(masks).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "inputs.npz"), **out)
+    print("inputs.npz", len(out))
+
+
 def gen_models(ref, only=None):
     for name in (only or MODEL_CASES):
         c = model_case(name)
@@ -227,7 +296,7 @@ def gen_grads(ref, name="hrnet32_k5_ctr", bpa_weight=0.35):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
-    which = sys.argv[1:] or ["losses", "distance", "rank", "rerank", "models", "grads", "masks"]
+    which = sys.argv[1:] or ["losses", "distance", "rank", "rerank", "inputs", "models", "grads", "masks"]
     if "losses" in which:
         gen_losses(ref)
     if "distance" in which:
@@ -236,6 +305,8 @@ if __name__ == "__main__":
         gen_rank(ref)
     if "rerank" in which:
         gen_rerank()
+    if "inputs" in which:
+        gen_inputs()
     if "models" in which:
         gen_models(ref)
     only = [w.split(":", 1)[1] for w in which if w.startswith("models:")]

@@ -137,6 +137,39 @@ def rerank_case(name):
     return dict(q_g=dist(qf, gf), q_q=dist(qf, qf), g_g=dist(gf, gf), k1=k1, k2=k2, lam=lam, q_pids=qid, g_pids=gid)
 
 
+# input pipeline (data/transforms.py:24-163, data/masks_transforms/mask_transform.py:21-85):
+# name -> (H, W, masks preprocess, background strategy, threshold, softmax weight, augment?)
+INPUT_CASES = {"test_384_five_v": (384, 128, "five_v", "threshold", 0.5, 15, False),
+               "train_256_eight": (256, 128, "eight", "threshold", 0.5, 15, True),
+               "test_256_diffmax": (256, 128, "five_v", "diff_from_max", 0.3, 15, False)}
+_INPUT_SIZES = [((128, 64), (16, 8)), ((200, 77), (25, 10)), ((51, 23), (33, 17)), ((384, 128), (48, 16)),
+                ((300, 150), (38, 19)), ((64, 32), (64, 32))]
+
+
+def input_case(name):
+    """A batch of RGB uint8 images of different sizes with their 36-channel pifpaf confidence stacks (float32, sparse)."""
+    h, w, prep, strat, thr, smw, aug = INPUT_CASES[name]
+    rs = np.random.RandomState(list(INPUT_CASES).index(name) + 91)
+    images, fields, params = [], [], []
+    for (ih, iw), (mh, mw) in _INPUT_SIZES:
+        images.append(rs.randint(0, 256, (ih, iw, 3)).astype(np.uint8))
+        f = rs.rand(36, mh, mw).astype(F32) * (rs.rand(36, mh, mw) > 0.6)
+        fields.append(f.astype(F32))
+        if aug:
+            flip = bool(rs.rand() < 0.5)
+            crop = (int(rs.randint(0, 21)), int(rs.randint(0, 21)))
+            erase = None
+            if rs.rand() < 0.7:                               # CoarseDropout geometry (transforms.py:112-117)
+                eh, ew = rs.randint(int(h * 0.15), int(h * 0.65) + 1), rs.randint(int(w * 0.15), int(w * 0.65) + 1)
+                y0, x0 = rs.randint(0, h - eh + 1), rs.randint(0, w - ew + 1)
+                erase = (int(x0), int(y0), int(x0 + ew), int(y0 + eh))
+            params.append(dict(flip=flip, crop=crop, erase=erase))
+        else:
+            params.append(dict(flip=False, crop=None, erase=None))
+    return dict(images=images, fields=fields, params=params, height=h, width=w, preprocess=prep, strategy=strat,
+                threshold=thr, softmax_weight=smw)
+
+
 MODEL_CASES = ["hrnet32_k5", "resnet50_k5", "ibn_k8", "hrnet32_k5_384", "hrnet32_k5_ctr"]
 # external part masks (bpbreid.py:149-175): name -> (base case, config overrides); eval-mode goldens with the masks passed
 MASK_CASES = {"hrnet32_k5_extattn": ("hrnet32_k5", dict(learnable_attention_enabled=False)),

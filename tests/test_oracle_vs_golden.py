@@ -148,3 +148,37 @@ def test_rerank_oracle_reproduces_reference_bit_for_bit(golden, name):
     c = GI.rerank_case(name)
     out = RO.re_ranking(c["q_g"], c["q_q"], c["g_g"], c["k1"], c["k2"], c["lam"])
     np.testing.assert_array_equal(out, golden("rerank")[f"{name}/final"])
+
+
+def test_input_oracle_resize_is_bit_exact_against_cv2():
+    """oracle/input_oracle.py restates cv2.resize (INTER_LINEAR on uint8, INTER_NEAREST index rule): pinned against cv2
+    itself (opencv-python 4.13 in this image; skipped where cv2 is absent)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import input_oracle as IO
+    rs = np.random.RandomState(0)
+    for (h, w, hh, ww) in [(128, 64, 256, 128), (128, 64, 384, 128), (200, 77, 256, 128), (51, 23, 256, 128),
+                           (37, 90, 64, 32), (300, 150, 256, 128), (500, 311, 384, 128), (256, 128, 256, 128),
+                           (1, 64, 1, 128), (64, 1, 128, 1), (255, 129, 256, 128)]:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        np.testing.assert_array_equal(IO.resize_linear_u8(img, hh, ww), cv2.resize(img, (ww, hh), interpolation=cv2.INTER_LINEAR))
+        m = rs.rand(h, w, 3).astype(np.float32)
+        yi, xi = IO.nearest_index_cv2(hh, h), IO.nearest_index_cv2(ww, w)
+        np.testing.assert_array_equal(m[yi][:, xi], cv2.resize(m, (ww, hh), interpolation=cv2.INTER_NEAREST).reshape(hh, ww, 3))
+
+
+@pytest.mark.parametrize("name", list(GI.INPUT_CASES))
+def test_input_oracle_reproduces_reference_transforms(golden, name):
+    """oracle/input_oracle.py vs tests/golden/inputs.npz (the reference's mask transform classes + cv2, composed in
+    build_transforms' order by oracle/make_golden.py inputs), and the product's restated group tables vs the reference's."""
+    from bpbreid_b200 import data
+    from oracle import input_oracle as IO
+    g = golden("inputs")
+    c = GI.input_case(name)
+    np.testing.assert_array_equal(data.group_table(c["preprocess"]), g["groups/" + c["preprocess"]])
+    groups = [np.nonzero(r)[0].tolist() for r in g["groups/" + c["preprocess"]]]
+    for i, (img, f, p) in enumerate(zip(c["images"], c["fields"], c["params"])):
+        x = IO.preprocess_image(img, c["height"], c["width"], (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), p["flip"], p["crop"], p["erase"])
+        m = IO.preprocess_masks(f, c["height"], c["width"], groups, 4, c["strategy"], c["threshold"], c["softmax_weight"],
+                                p["flip"], p["crop"], p["erase"])
+        np.testing.assert_array_equal(x, g[f"{name}/images"][i])
+        np.testing.assert_array_equal(m, g[f"{name}/masks"][i])
