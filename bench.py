@@ -295,6 +295,32 @@ def eval_config5(dev, peaks, nq=4096, ng=16384, p=6, d=512, reps=5):
             "pairs_per_s": nq * ng / ((d_ms + r_ms) * 1e-3)}
 
 
+def input_pipeline_leg(dev, batch=256):
+    """decoded Market-1501-sized samples (RGB uint8 128x64 + 36 pifpaf fields 16x8) -> model inputs at
+    384x128 (every shipped YAML's size) through bpbreid_b200.data.DeviceInputPipeline: host packing into pinned memory,
+    one H2D copy per stream of samples, two kernel launches; timed end to end on the host clock around a device sync."""
+    from bpbreid_b200 import data
+    rs = np.random.RandomState(0)
+    images = [rs.randint(0, 256, (128, 64, 3)).astype(np.uint8) for _ in range(batch)]
+    fields = [rs.rand(36, 16, 8).astype(np.float32) for _ in range(batch)]
+    pipe = data.DeviceInputPipeline(384, 128, transforms=["rc", "re"], masks_preprocess="five_v", device=dev)
+    params = pipe.draw_params(batch, np.random.RandomState(1))
+    for _ in range(2):
+        pipe(images, fields, params)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        pipe(images, fields, params)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    ms = float(np.median(ts)) * 1e3
+    k_ms = _cuda_time(lambda: pipe(images, fields, params), 3)
+    return {"value": batch / (ms * 1e-3), "unit": "images/s", "ms_per_batch": ms, "batch": batch,
+            "what": "uint8 128x64 + 36x16x8 fields -> [N,3,384,128] f32 + [N,6,96,32] masks; host pack + H2D + 2 kernels "
+                    "(wall clock); cv2-exact resize", "ms_incl_pack_device_timed": k_ms}
+
+
 def library_baseline(dev, batch, h):
     """The reference port on ATen / cuDNN (bf16 autocast, channels_last) on the same GPU: forward + GiLt, same batch.
     This is what the reference would run on this machine (it ships no kernels of its own)."""
@@ -578,6 +604,10 @@ def run_gpu_arm(args, rank, world):
             except Exception as e:
                 extras["eval_forward"] = {"error": repr(e)[:300]}
             torch.cuda.empty_cache()
+            try:
+                extras["input_pipeline"] = input_pipeline_leg(dev)
+            except Exception as e:
+                extras["input_pipeline"] = {"error": repr(e)[:300]}
             try:
                 extras["eval_config5"] = eval_config5(dev, peaks)
             except Exception as e:
