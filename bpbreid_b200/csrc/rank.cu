@@ -220,7 +220,7 @@ int rank_market1501(const float* dist, const int64_t* q_pids, const int64_t* g_p
 
 // ----------------------------------------------------------------------------------------------
 // Stable ascending argsort of every row (ties -> ascending index), bitonic network in shared memory on
-// 64-bit keys (ordered float bits << 32 | index).  One CTA per row; Ng <= 16384.
+// 64-bit keys (ordered float bits << 32 | index).  One CTA per row; Ng <= 16384 (split arrays up to 32768, below).
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ordered_bits(float f) {
     if (f == 0.f) f = 0.f;                       // -0.0 == +0.0 for comparison sorts
@@ -252,13 +252,52 @@ __global__ void __launch_bounds__(1024) argsort_rows_kernel(const float* __restr
     for (int j = threadIdx.x; j < ng; j += blockDim.x) out[j] = static_cast<int32_t>(keys[j] & 0xFFFFFFFFu);
 }
 
+// Same network for 16384 < Ng <= 32768 (Market-1501's gallery has 19 732 entries, DukeMTMC 17 661): the 64-bit keys no
+// longer fit, so the ordered float bits and the 16-bit column index live in two shared arrays (192 KB) and are compared
+// lexicographically.
+__global__ void __launch_bounds__(1024) argsort_rows_split_kernel(const float* __restrict__ dist, int ng, int npow2,
+                                                                  int32_t* __restrict__ indices) {
+    extern __shared__ uint32_t skeys[];
+    uint16_t* sidx = reinterpret_cast<uint16_t*>(skeys + npow2);
+    const float* row = dist + static_cast<int64_t>(blockIdx.x) * ng;
+    for (int j = threadIdx.x; j < npow2; j += blockDim.x) {
+        skeys[j] = j < ng ? ordered_bits(row[j]) : 0xFFFFFFFFu;
+        sidx[j] = static_cast<uint16_t>(j);                   // padding sorts behind every real entry with the same key
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < npow2 / 2; t += blockDim.x) {
+                const int lo = ((t / j) * 2 * j) + (t % j);
+                const int hi = lo + j;
+                const bool up = (lo & k) == 0;
+                const uint32_t ka = skeys[lo], kb = skeys[hi];
+                const uint16_t ia = sidx[lo], ib = sidx[hi];
+                const bool gt = ka > kb || (ka == kb && ia > ib);
+                if (gt == up) { skeys[lo] = kb; skeys[hi] = ka; sidx[lo] = ib; sidx[hi] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    int32_t* out = indices + static_cast<int64_t>(blockIdx.x) * ng;
+    for (int j = threadIdx.x; j < ng; j += blockDim.x) out[j] = static_cast<int32_t>(sidx[j]);
+}
+
 int argsort_rows(const float* dist, int nq, int ng, int32_t* indices, cudaStream_t stream) {
     int npow2 = 1;
     while (npow2 < ng) npow2 <<= 1;
-    BPB_CHECK(npow2 <= 16384, "argsort_rows: Ng=%d exceeds the 16384-entry shared-memory sorter", ng);
-    const size_t smem = static_cast<size_t>(npow2) * sizeof(uint64_t);
-    BPB_SET_MAX_SMEM(argsort_rows_kernel, 128 * 1024);
-    argsort_rows_kernel<<<nq, 1024, smem, stream>>>(dist, ng, npow2, indices);
+    BPB_CHECK(npow2 <= 32768, "argsort_rows: Ng=%d exceeds the 32768-entry shared-memory sorter", ng);
+    if (npow2 <= 16384) {
+        const size_t smem = static_cast<size_t>(npow2) * sizeof(uint64_t);
+        BPB_SET_MAX_SMEM(argsort_rows_kernel, 128 * 1024);
+        argsort_rows_kernel<<<nq, 1024, smem, stream>>>(dist, ng, npow2, indices);
+    } else {
+        // a real entry with key 0xFFFFFFFF (a NaN with all payload bits set) would tie with the padding: indices of the
+        // padding are >= ng and still sort behind it, so the first ng outputs are the real entries
+        const size_t smem = static_cast<size_t>(npow2) * (sizeof(uint32_t) + sizeof(uint16_t));
+        BPB_SET_MAX_SMEM(argsort_rows_split_kernel, 192 * 1024);
+        argsort_rows_split_kernel<<<nq, 1024, smem, stream>>>(dist, ng, npow2, indices);
+    }
     BPB_LAUNCH_CHECK("argsort_rows_kernel");
     return 0;
 }

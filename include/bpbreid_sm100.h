@@ -191,7 +191,7 @@ int bpb_rank_market1501(const float* dist, const int64_t* q_pids, const int64_t*
                         const int64_t* g_camids, int nq, int ng, int max_rank, double* ap64, float* ap32,
                         int* first_rank, float* cmc, double* map_out, int64_t* num_valid, float* map32_out,
                         int* overflow_flag, void* stream);
-/* Stable ascending argsort of every row (== np.argsort(kind='stable')); ng <= 16384. */
+/* Stable ascending argsort of every row (== np.argsort(kind='stable')); ng <= 32768 (Market-1501: 19 732). */
 int bpb_argsort_rows(const float* dist, int nq, int ng, int32_t* indices, void* stream);
 
 /* ---- training backward: replaces autograd's `loss.backward()` + `optimizer.step()` for this path

@@ -361,6 +361,55 @@ def test_map_parity_on_synthetic_gallery_from_model_embeddings(golden):
     assert abs(r_c["mAP"] - r_o["mAP"]) < 1e-12
 
 
+def test_end_to_end_map_cuda_distance_and_rank_vs_reference_distance_and_rank():
+    """Reference chain (fp32 distance oracle -> numpy ranking) against the CUDA chain (bpb_part_distance ->
+    bpb_rank_market1501) on the SAME features: identity-clustered synthetic gallery, bool visibility.  The SIMT fp32
+    distance (impl=1) must give identical CMC and mAP; the tcgen05 path feeds tf32-rounded operands (errors up to 2e-3
+    on a distance of ~1), which may swap near-equal neighbours: its CMC / mAP are asserted to the measured bound and the
+    number of differing rank positions is reported."""
+    rs = np.random.RandomState(21)
+    nid, p, d, nq, ng = 40, 6, 512, 128, 1024
+    cen = rs.randn(nid, p, d).astype(np.float32)
+
+    def feats(n):
+        ids = rs.randint(0, nid, n)
+        f = cen[ids] + 1.5 * rs.randn(n, p, d).astype(np.float32)
+        return (f / np.linalg.norm(f, axis=-1, keepdims=True)).astype(np.float32), ids, rs.rand(n, p) > 0.2
+    (qf, qid, qv), (gf, gid, gv) = feats(nq), feats(ng)
+    qc, gc = rs.randint(0, 3, nq), rs.randint(0, 3, ng)
+    d_ref, _ = MO.part_distance(qf, gf, qv, gv)
+    r_ref = MO.eval_market1501(d_ref, qid, gid, qc, gc, 50)
+    rep = []
+    for impl, name in ((1, "simt fp32"), (0, "tcgen05 tf32")):
+        d_c, _ = metrics.part_distance_device(torch.from_numpy(qf).to(DEV), torch.from_numpy(gf).to(DEV),
+                                              torch.from_numpy(qv).to(DEV), torch.from_numpy(gv).to(DEV), impl=impl)
+        r_c = metrics.evaluate_rank(d_c.cpu().numpy(), qid, gid, qc, gc, 50)
+        swaps = int((np.argsort(d_c.cpu().numpy(), 1, kind="stable") != np.argsort(d_ref, 1, kind="stable")).sum())
+        rep.append(f"{name}: max |d - d_ref| {np.abs(d_c.cpu().numpy() - d_ref).max():.2e}, differing rank positions "
+                   f"{swaps} of {nq * ng}, |cmc diff| {np.abs(r_c['cmc'] - r_ref['cmc']).max():.2e}, "
+                   f"mAP {r_c['mAP']:.6f} vs reference {r_ref['mAP']:.6f}")
+        if impl == 1:
+            np.testing.assert_allclose(r_c["cmc"], r_ref["cmc"], atol=1e-7)
+            assert abs(r_c["mAP"] - r_ref["mAP"]) < 1e-6, rep
+        else:
+            assert np.abs(r_c["cmc"] - r_ref["cmc"]).max() <= 1.0 / nq + 1e-7 and abs(r_c["mAP"] - r_ref["mAP"]) < 1e-3, rep
+    print("\n".join(rep))
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    open("gpurun_out/map_e2e_report.txt", "w").write("\n".join(rep) + "\n")
+
+
+def test_argsort_rows_beyond_16384_entries():
+    """Market-1501's gallery has 19 732 entries: the split-array sorter (keys + 16-bit indices) == np.argsort(stable),
+    including massive tie groups."""
+    rs = np.random.RandomState(2)
+    d = rs.rand(6, 19732).astype(np.float32)
+    d[1] = np.round(d[1] * 8) / 8
+    d[2, :5000] = 2.0
+    idx = metrics.argsort_rows(torch.from_numpy(d).to(DEV)).cpu().numpy()
+    np.testing.assert_array_equal(idx, np.argsort(d, axis=1, kind="stable"))
+
+
 @pytest.mark.parametrize("name", list(GI.MASK_CASES))
 def test_external_part_masks_match_reference_golden(golden, name):
     """External part masks (bpbreid.py:149-175): attention taken from the masks (learnable_attention_enabled False), and
