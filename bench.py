@@ -315,10 +315,9 @@ def input_pipeline_leg(dev, batch=256):
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
     ms = float(np.median(ts)) * 1e3
-    k_ms = _cuda_time(lambda: pipe(images, fields, params), 3)
     return {"value": batch / (ms * 1e-3), "unit": "images/s", "ms_per_batch": ms, "batch": batch,
             "what": "uint8 128x64 + 36x16x8 fields -> [N,3,384,128] f32 + [N,6,96,32] masks; host pack + H2D + 2 kernels "
-                    "(wall clock); cv2-exact resize", "ms_incl_pack_device_timed": k_ms}
+                    "(wall clock); cv2-exact resize"}
 
 
 def library_baseline(dev, batch, h):
@@ -676,6 +675,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly (kernel-by-kernel profiling)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-library", action="store_true")
+    ap.add_argument("--lib", default=None, help="A/B aid: load this build of libbpbreid_sm100.so instead of the in-tree one")
     ap.add_argument("--profile", action="store_true",
                     help="run ONE step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -690,6 +690,9 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
+    if args.lib:
+        from bpbreid_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(args.lib)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
     run_gpu_arm(args, rank, world)
