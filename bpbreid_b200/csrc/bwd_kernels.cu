@@ -536,31 +536,31 @@ __global__ void __launch_bounds__(256) stem_wgrad3_kernel(const float* __restric
                                                           int n, int h, int wd, int stride, int ho, int wo) {
     constexpr int kTaps = 27, kPix = 64;
     __shared__ __align__(16) float s_dy[kPix][64];            // reused for the cross-phase reduction at the end
-    __shared__ __align__(16) float s_img[kPix][32];           // [px][tap group][8]: tap t -> slot (t / 7) * 8 + t % 7
+    __shared__ float s_img[32][kPix];                         // [slot][px]: tap t -> slot (t / 7) * 8 + t % 7
+    __shared__ int s_base[kPix], s_iy[kPix], s_ix[kPix];      // per pixel: image plane offset, top-left input coords
     const int cg = threadIdx.x & 15, tg = (threadIdx.x >> 4) & 3, ph = threadIdx.x >> 6;
     float acc[4][8];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+    for (int i = threadIdx.x; i < 32 * kPix; i += 256) (&s_img[0][0])[i] = 0.f;     // padding slots stay zero
     const int64_t total = static_cast<int64_t>(n) * ho * wo;
+    const int hw_out = ho * wo;
     for (int64_t base = static_cast<int64_t>(blockIdx.x) * kPix; base < total;
          base += static_cast<int64_t>(gridDim.x) * kPix) {
         __syncthreads();
-        for (int i = threadIdx.x; i < kPix * 32; i += 256) {
-            const int px = i >> 5, slot = i & 31;
-            const int tp = (slot >> 3) * 7 + (slot & 7);
-            const int64_t pix = base + px;
-            float v = 0.f;
-            if ((slot & 7) < 7 && tp < kTaps && pix < total) {
-                const int ox = pix % wo, oy = (pix / wo) % ho, im = pix / (static_cast<int64_t>(wo) * ho);
-                const int ci = tp / 9, r = (tp / 3) % 3, sx = tp % 3;
-                const int iy = oy * stride + r - 1, ix = ox * stride + sx - 1;
-                if (iy >= 0 && iy < h && ix >= 0 && ix < wd)
-                    // the forward consumed the image at bf16 precision (stem_conv_kernel)
-                    v = __bfloat162float(__float2bfloat16(img[((static_cast<int64_t>(im) * 3 + ci) * h + iy) * wd + ix]));
+        if (threadIdx.x < kPix) {                                 // pixel coordinates once per pixel (no per-tap division)
+            const int64_t pix = base + threadIdx.x;
+            if (pix < total) {
+                const int im = static_cast<int>(pix / hw_out), rem = static_cast<int>(pix - static_cast<int64_t>(im) * hw_out);
+                const int oy = rem / wo, ox = rem - oy * wo;
+                s_base[threadIdx.x] = im * 3 * h * wd;
+                s_iy[threadIdx.x] = oy * stride - 1;
+                s_ix[threadIdx.x] = ox * stride - 1;
+            } else {
+                s_base[threadIdx.x] = -1;
             }
-            s_img[px][slot] = v;
         }
         for (int i = threadIdx.x; i < kPix * 8; i += 256) {       // 8 channels (16 bytes of bf16) per thread
             const int px = i >> 3, c8 = i & 7;
@@ -571,13 +571,28 @@ __global__ void __launch_bounds__(256) stem_wgrad3_kernel(const float* __restric
             for (int t = 0; t < 8; ++t) s_dy[px][c8 * 8 + t] = f[t];
         }
         __syncthreads();
+        // lanes walk consecutive pixels of one tap: stride-`stride` reads of one image row, conflict-free stores
+        for (int i = threadIdx.x; i < kTaps * kPix; i += 256) {
+            const int tp = i >> 6, px = i & 63;
+            const int ci = tp / 9, r = (tp / 3) % 3, sx = tp % 3;
+            float v = 0.f;
+            const int b0 = s_base[px];
+            if (b0 >= 0) {
+                const int iy = s_iy[px] + r, ix = s_ix[px] + sx;
+                if (iy >= 0 && iy < h && ix >= 0 && ix < wd)
+                    // the forward consumed the image at bf16 precision (stem_conv_kernel)
+                    v = __bfloat162float(__float2bfloat16(img[static_cast<size_t>(b0) + (static_cast<size_t>(ci) * h + iy) * wd + ix]));
+            }
+            s_img[(tp / 7) * 8 + tp % 7][px] = v;
+        }
+        __syncthreads();
 #pragma unroll 4
         for (int px = ph; px < kPix; px += 4) {
             const float4 d = *reinterpret_cast<const float4*>(&s_dy[px][cg * 4]);
-            const float4 a0 = *reinterpret_cast<const float4*>(&s_img[px][tg * 8]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&s_img[px][tg * 8 + 4]);
             const float dv[4] = {d.x, d.y, d.z, d.w};
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float av[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) av[b] = s_img[tg * 8 + b][px];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
