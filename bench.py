@@ -91,9 +91,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_cfg():
+IBN_BACKBONE = "fastreid_resnet_ibn"
+
+
+def make_cfg(backbone="hrnet32", parts=K_PARTS):
     from bpbreid_b200.config import make_cfg as mk
-    return mk("hrnet32", K_PARTS)
+    return mk(backbone, parts)
 
 
 def synth_batch(n, seed, h=256, w=128):
@@ -295,6 +298,40 @@ def eval_config5(dev, peaks, nq=4096, ng=16384, p=6, d=512, reps=5):
             "pairs_per_s": nq * ng / ((d_ms + r_ms) * 1e-3)}
 
 
+def eval_end_to_end_leg(dev, nq=3368, ng=15913, batch=256):
+    """The whole evaluation (part_based_engine.py:168-295) at Market-1501 scale through the engine mirror: feature extraction
+    of nq + ng images (H2D from pinned host memory every batch), L2 normalisation, part distance, k-reciprocal re-ranking
+    (q-q, g-g distances included), CMC / mAP -- everything after the copy stays on the device.  Wall clock around a sync."""
+    from bpbreid_b200 import engine, models
+    torch.manual_seed(0)
+    cfg = make_cfg()
+    m = models.build_model("bpbreid", num_classes=NUM_CLASSES, loss="part_based", pretrained=False, use_gpu=True,
+                           config=cfg).to(dev).eval()
+    m.use_cuda_graph = True
+    m.materialize_spatial_features = False
+    eng = engine.ImagePartBasedEngine(model=m, config=cfg, mask_filtering_testing=True)
+    host = synth_batch(batch, 5, 256, 128)[0].pin_memory()
+    rs = np.random.RandomState(0)
+
+    def loader(n, cams):
+        for lo in range(0, n, batch):
+            k = min(batch, n - lo)
+            yield {"image": host[:k], "pid": rs.randint(0, 751, k), "camid": rs.randint(*cams, k)}
+    out = {}
+    for rerank in (False, True):
+        for _ in range(2):                                          # first pass builds the plans / graphs
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            cmc, m_ap = eng._evaluate(loader(nq, (0, 3)), loader(ng, (3, 6)), normalize_feature=True, rerank=rerank)
+            torch.cuda.synchronize()
+            sec = time.perf_counter() - t0
+        out["with_rerank_s" if rerank else "seconds"] = sec
+    out.update({"images": nq + ng, "images_per_s": (nq + ng) / out["seconds"],
+                "what": f"{nq} query + {ng} gallery images: extraction (eval mode, fused epilogues, H2D per batch) + "
+                        "normalise + part distance + CMC/mAP, device-resident; second figure adds k-reciprocal re-ranking"})
+    return out
+
+
 def input_pipeline_leg(dev, batch=256):
     """decoded Market-1501-sized samples (RGB uint8 128x64 + 36 pifpaf fields 16x8) -> model inputs at
     384x128 (every shipped YAML's size) through bpbreid_b200.data.DeviceInputPipeline: host packing into pinned memory,
@@ -372,13 +409,13 @@ def library_baseline(dev, batch, h):
 class FwdLoss:
     """forward + GiLt loss through the public API (models.build_model / losses.GiLtLoss / distributed_gilt)."""
 
-    def __init__(self, dev, batch, h, rank, world, use_graph=True):
+    def __init__(self, dev, batch, h, rank, world, use_graph=True, backbone="hrnet32", parts=K_PARTS):
         from bpbreid_b200 import distributed as D
         from bpbreid_b200 import losses, models
         torch.manual_seed(0)
         self.D, self.world = D, world
         self.model = models.build_model("bpbreid", num_classes=NUM_CLASSES, loss="part_based", pretrained=False,
-                                        use_gpu=True, config=make_cfg()).to(dev)
+                                        use_gpu=True, config=make_cfg(backbone, parts)).to(dev)
         self.model.train()
         self.model.use_cuda_graph = use_graph
         self.model.materialize_spatial_features = False      # the 1920-ch map is an unused *output* of forward+loss
@@ -582,6 +619,17 @@ def run_gpu_arm(args, rank, world):
             except Exception as e:
                 extras["config2_bs64_384x128"] = {"error": repr(e)[:300]}
             torch.cuda.empty_cache()
+            try:                                             # BASELINE config 4's per-GPU share (512 / 8), in bf16
+                c4 = FwdLoss(dev, 64, 256, rank, world, backbone=IBN_BACKBONE, parts=8)
+                ms, l = quick(c4, dev, world)
+                extras["config4_ibn_k8_bs64_per_gpu"] = {
+                    "value": 64 / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "loss": l,
+                    "what": "fast-reid ResNet-50-IBN, K=8, 256x128, forward + GiLt, batch 64 = one GPU's share of config 4 "
+                            "(bs512 on 8 GPUs); bf16 activations (the reference config says fp16: not built)"}
+                del c4
+            except Exception as e:
+                extras["config4_ibn_k8_bs64_per_gpu"] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
             try:
                 from bpbreid_b200 import models
                 torch.manual_seed(0)
@@ -602,6 +650,11 @@ def run_gpu_arm(args, rank, world):
                 del me, xe
             except Exception as e:
                 extras["eval_forward"] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+            try:
+                extras["eval_end_to_end_market_scale"] = eval_end_to_end_leg(dev)
+            except Exception as e:
+                extras["eval_end_to_end_market_scale"] = {"error": repr(e)[:300]}
             torch.cuda.empty_cache()
             try:
                 extras["input_pipeline"] = input_pipeline_leg(dev)

@@ -30,16 +30,21 @@ def test_input_pipeline_matches_reference_golden(golden, name):
     assert abs(float(masks.sum(1).mean()) - 1.0) < 1e-5                 # softmax rows
 
 
-def test_input_pipeline_random_sizes_vs_oracle():
-    """Odd source sizes (up- and down-scaling on both axes, 1-pixel-wide sources) against the oracle, which is pinned
-    bit-for-bit to cv2.resize by the CPU suite."""
+@pytest.mark.parametrize("strategy,softmax_weight,combine", [("threshold", 15, "max"), ("sum", 0, "sum"),
+                                                             ("diff_from_max", 4, "max")])
+def test_input_pipeline_random_sizes_vs_oracle(strategy, softmax_weight, combine):
+    """Odd source sizes (up- and down-scaling on both axes, 1-pixel-wide sources), every background strategy, both
+    combine modes and the softmax-free normalisation (mask_transform.py:80-83, 0/0 -> NaN like the reference) against the
+    oracle, which is pinned bit-for-bit to cv2.resize and to the reference's mask classes by the CPU suite."""
     from bpbreid_b200 import data
     rs = np.random.RandomState(9)
     sizes = [(17, 300), (301, 9), (1, 64), (64, 1), (255, 129), (256, 128), (700, 333), (96, 48)]
     images = [rs.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in sizes]
     fields = [(rs.rand(36, max(h // 7, 1), max(w // 7, 1)) * (rs.rand(36, max(h // 7, 1), max(w // 7, 1)) > 0.5)).astype(np.float32)
               for h, w in sizes]
-    pipe = data.DeviceInputPipeline(256, 128, transforms=["rf", "rc", "re"], masks_preprocess="five_v", device=DEV)
+    pipe = data.DeviceInputPipeline(256, 128, transforms=["rf", "rc", "re"], masks_preprocess="five_v", device=DEV,
+                                    background_computation_strategy=strategy, softmax_weight=softmax_weight,
+                                    combine_mode=combine)
     params = pipe.draw_params(len(images), np.random.RandomState(4))
     imgs, masks = pipe(images, fields, params)
     torch.cuda.synchronize()
@@ -47,9 +52,10 @@ def test_input_pipeline_random_sizes_vs_oracle():
     groups = [np.nonzero(r)[0].tolist() for r in tab]
     for i, (im, f, p) in enumerate(zip(images, fields, params)):
         ref_i = IO.preprocess_image(im, 256, 128, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), p["flip"], p["crop"], p["erase"])
-        ref_m = IO.preprocess_masks(f, 256, 128, groups, 4, "threshold", 0.5, 15, p["flip"], p["crop"], p["erase"])
+        ref_m = IO.preprocess_masks(f, 256, 128, groups, 4, strategy, 0.5, softmax_weight, p["flip"], p["crop"], p["erase"],
+                                    combine=combine)
         np.testing.assert_array_equal(imgs[i].cpu().numpy(), ref_i)
-        assert np.abs(masks[i].cpu().numpy() - ref_m).max() < 1e-6
+        np.testing.assert_allclose(masks[i].cpu().numpy(), ref_m, rtol=0, atol=1e-6, equal_nan=True)
 
 
 def test_input_pipeline_feeds_the_model():
