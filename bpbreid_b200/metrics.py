@@ -61,8 +61,9 @@ def part_distance_device(qf, gf, qv=None, gv=None, dist_combine_strat="mean", me
 
 def compute_distance_matrix_using_bp_features(qf, gf, qf_parts_visibility=None, gf_parts_visibility=None,
                                               dist_combine_strat="mean", batch_size_pairwise_dist_matrix=5000,
-                                              use_gpu=False, metric="euclidean"):
-    """Reference signature.  `batch_size_pairwise_dist_matrix` only bounded the reference's memory (gallery
+                                              use_gpu=False, metric="euclidean", exact=False):
+    """Reference signature (+ `exact`: the SIMT fp32 distance path instead of the tcgen05 tf32 one, for evaluations that
+    must be rank-for-rank comparable with the fp32 reference).  `batch_size_pairwise_dist_matrix` only bounded the reference's memory (gallery
     chunks + a D2H copy per chunk); one fused launch covers the whole matrix here, so it is accepted and ignored.
     `use_gpu` is accepted for compatibility: the computation always runs on the GPU."""
     dev = _device()
@@ -70,7 +71,7 @@ def compute_distance_matrix_using_bp_features(qf, gf, qf_parts_visibility=None, 
     g = gf.to(dev, non_blocking=True)
     qv = None if qf_parts_visibility is None else qf_parts_visibility.to(dev, non_blocking=True)
     gv = None if gf_parts_visibility is None else gf_parts_visibility.to(dev, non_blocking=True)
-    dist, part = part_distance_device(q, g, qv, gv, dist_combine_strat, metric)
+    dist, part = part_distance_device(q, g, qv, gv, dist_combine_strat, metric, impl=1 if exact else 0)
     return dist.cpu(), part.cpu()
 
 

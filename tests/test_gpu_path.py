@@ -399,6 +399,29 @@ def test_end_to_end_map_cuda_distance_and_rank_vs_reference_distance_and_rank():
     open("gpurun_out/map_e2e_report.txt", "w").write("\n".join(rep) + "\n")
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_masked_sentinel_value_with_ragged_query_tiles(metric, impl):
+    """Nq not a multiple of the 128-row tile, non-negative un-normalised features, cosine and euclidean: the
+    rows of the last query tile beyond Nq (TMA zero fill) must not leak into max(part_dist) + 1, the value every masked
+    entry is rewritten to (distance.py:173-176)."""
+    rs = np.random.RandomState(12)
+    nq, ng, p, d = 200, 300, 6, 64
+    qf = (rs.rand(nq, p, d) * 0.05).astype(np.float32)           # small norms: a leaked |g| or 1.0 would dominate
+    gf = (rs.rand(ng, p, d) * 3.0).astype(np.float32)
+    qv, gv = rs.rand(nq, p) > 0.3, rs.rand(ng, p) > 0.3
+    d_o, p_o = MO.part_distance(qf, gf, qv, gv, "mean", metric)
+    d_c, p_c = metrics.part_distance_device(torch.from_numpy(qf).to(DEV), torch.from_numpy(gf).to(DEV),
+                                            torch.from_numpy(qv).to(DEV), torch.from_numpy(gv).to(DEV), "mean", metric, impl=impl)
+    p_c, d_c = p_c.cpu().numpy(), d_c.cpu().numpy()
+    masked = ~(qv.T[:, :, None] & gv.T[:, None, :])
+    tol = 2e-3 if impl == 0 else 1e-5
+    assert abs(float(p_c[masked].max()) - float(p_o[masked].max())) < tol * max(1.0, float(p_o.max()))   # the sentinel itself
+    assert (p_c[masked] == p_c[masked].max()).all()
+    np.testing.assert_allclose(p_c, p_o, rtol=tol, atol=tol * max(1.0, float(p_o.max())))
+    np.testing.assert_allclose(d_c, d_o, rtol=tol, atol=tol * max(1.0, float(p_o.max())))
+
+
 def test_argsort_rows_beyond_16384_entries():
     """Market-1501's gallery has 19 732 entries: the split-array sorter (keys + 16-bit indices) == np.argsort(stable),
     including massive tie groups."""
