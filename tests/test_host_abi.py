@@ -114,3 +114,41 @@ def test_extract_test_embeddings_matches_reference_semantics():
     assert f.shape == (n, K + 1, D) and v.shape == (n, K + 1) and pm.shape == (n, K + 1, 4, 2) and pix == "pix"
     assert torch.equal(f[:, 0], emb["bn_foreg"]) and torch.equal(f[:, 1:], emb["parts"])
     assert torch.equal(v[:, 0], vis["foreg"])                              # bn_foreg takes the visibility of foreg
+
+
+def test_input_pipeline_host_logic():
+    """bpbreid_b200.data: group tables, parameter draws and error behaviour (no device needed)."""
+    import numpy as np
+    from bpbreid_b200 import data
+    t5, t8 = data.group_table("five_v"), data.group_table("eight")
+    assert t5.shape == (5, 36) and t8.shape == (8, 36) and t5.sum() == 36 and t8.sum() == 36 + 1  # 'eight' shares one joint
+    with pytest.raises(KeyError):
+        data.group_table("eleven")
+    pipe = data.DeviceInputPipeline(384, 128, transforms=["rf", "rc", "re"], masks_preprocess="five_v", device="cuda:0")
+    assert (pipe.out_h, pipe.out_w, pipe.parts_num) == (96, 32, 5) and len(pipe.parts_names) == 5
+    ps = pipe.draw_params(400, np.random.RandomState(0))
+    assert 0.35 < np.mean([p["flip"] for p in ps]) < 0.65 and 0.35 < np.mean([p["erase"] is not None for p in ps]) < 0.65
+    for p in ps:
+        assert 0 <= p["crop"][0] <= 20 and 0 <= p["crop"][1] <= 20
+        if p["erase"] is not None:
+            x0, y0, x1, y1 = p["erase"]
+            assert 0 <= x0 < x1 <= 128 and 0 <= y0 < y1 <= 384
+            assert int(128 * 0.15) <= x1 - x0 <= int(128 * 0.65) and int(384 * 0.15) <= y1 - y0 <= int(384 * 0.65)
+    test_only = data.DeviceInputPipeline(256, 128, transforms=None, device="cuda:0")
+    assert all(p == dict(flip=False, crop=None, erase=None) for p in test_only.draw_params(3, np.random.RandomState(1)))
+    with pytest.raises(ValueError):
+        data.DeviceInputPipeline(256, 128, background_computation_strategy="median", device="cuda:0")
+    with pytest.raises(NotImplementedError):
+        data.DeviceInputPipeline(256, 128, transforms=["random_occlusion"], device="cuda:0")
+
+
+def test_rerank_rejects_cpu_inputs_without_a_device():
+    """re_ranking has no CPU path: on a box without CUDA it must raise, never fall back (prompt, section 3)."""
+    import numpy as np
+    import torch
+    from bpbreid_b200 import rerank
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present: covered by tests/test_gpu_rerank.py")
+    d = np.zeros((2, 3), np.float32)
+    with pytest.raises(RuntimeError):
+        rerank.re_ranking(d, np.zeros((2, 2), np.float32), np.zeros((3, 3), np.float32))
