@@ -33,6 +33,45 @@ int check_cuda(cudaError_t e, const char* what);
         if (::bpb::check_cuda((call), #call)) return 2;            \
     } while (0)
 
+// Programmatic dependent launch: a kernel launched through launch_pdl may be scheduled while its predecessor in the stream
+// is still running; it must execute pdl_wait() before it touches anything the predecessor (or any earlier kernel) wrote.
+// pdl_trigger() in the predecessor allows that early scheduling (it is implied at exit).  Both are no-ops for kernels
+// launched the ordinary way.  The point is to hide the ~2 us launch + prologue (barrier init, TMEM allocation, descriptor
+// prefetch) of every kernel of a dependent chain behind the tail of the previous one.
+#ifndef BPB_PDL
+#define BPB_PDL 1
+#endif
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() {
+#if BPB_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#if BPB_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// `allow`: measured on the HRNet step (profiles/pdl_ab_r2.txt), early scheduling pays when the kernels of a chain are short
+// (batch 32 per GPU: 3.79 -> 3.49 ms per step) and costs ~0.6 % when they are long (batch 256: the waiting CTAs of the
+// next kernel hold shared memory / TMEM of SMs the running kernel could still use), so callers pass a size test.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool allow, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (BPB_PDL && allow) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define BPB_LAUNCH_CHECK(name)                                     \
     do {                                                           \
         if (::bpb::check_cuda(cudaGetLastError(), name)) return 3; \

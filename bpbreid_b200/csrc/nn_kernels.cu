@@ -329,6 +329,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                                                        const float* __restrict__ rscale,
                                                        const float* __restrict__ rshift, uint4* __restrict__ y,
                                                        int m, int cvec, int relu) {
+    pdl_trigger();
+    pdl_wait();
     const int width = cvec < 256 ? cvec : 256;
     const int rows_per_block = 256 / width;
     const int tx = threadIdx.x % width, ty = threadIdx.x / width;
@@ -408,9 +410,12 @@ int bn_apply(const void* x, const float* scale, const float* shift, const void* 
               "bn_apply: scale / shift vectors must be 16-byte aligned");
     int blocks = ceil_div(m, static_cast<int64_t>(rows_per_block) * 4);   // one unrolled four-row trip per thread at least
     if (blocks > 148 * 8) blocks = 148 * 8;
-    bn_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), scale, shift,
-                                                reinterpret_cast<const uint4*>(res), res_scale, res_shift,
-                                                reinterpret_cast<uint4*>(y), static_cast<int>(m), cvec, relu);
+    const bool pdl = m * c * 2 <= (8ll << 20);                      // short passes only (see launch_pdl)
+    if (check_cuda(launch_pdl(pdl, bn_apply_kernel, dim3(blocks), dim3(256), 0, stream, reinterpret_cast<const uint4*>(x), scale,
+                              shift, reinterpret_cast<const uint4*>(res), res_scale, res_shift,
+                              reinterpret_cast<uint4*>(y), static_cast<int>(m), cvec, relu),
+                   "bn_apply_kernel"))
+        return 3;
     BPB_LAUNCH_CHECK("bn_apply_kernel");
     return 0;
 }
@@ -429,6 +434,8 @@ struct FuseArgs {
 
 __global__ void __launch_bounds__(256) fuse_sum_kernel(FuseArgs a, uint4* __restrict__ y, int n, int h, int wd, int cvec,
                                                        int relu) {
+    pdl_trigger();
+    pdl_wait();
     const int width = cvec < 256 ? cvec : 256;
     const int rows_per_block = 256 / width;
     const int tx = threadIdx.x % width, ty = threadIdx.x / width;
@@ -484,7 +491,11 @@ int fuse_sum(const void* const* srcs, const float* const* scales, const float* c
     const int rows_per_block = 256 / (cvec < 256 ? cvec : 256);
     int blocks = ceil_div(static_cast<int64_t>(n) * h * wd, rows_per_block);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    fuse_sum_kernel<<<blocks, 256, 0, stream>>>(a, reinterpret_cast<uint4*>(y), n, h, wd, cvec, relu);
+    const bool pdl = static_cast<int64_t>(n) * h * wd * c * 2 <= (8ll << 20);
+    if (check_cuda(launch_pdl(pdl, fuse_sum_kernel, dim3(blocks), dim3(256), 0, stream, a, reinterpret_cast<uint4*>(y), n, h, wd,
+                              cvec, relu),
+                   "fuse_sum_kernel"))
+        return 3;
     BPB_LAUNCH_CHECK("fuse_sum_kernel");
     return 0;
 }

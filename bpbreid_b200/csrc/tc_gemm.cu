@@ -133,6 +133,10 @@ __global__ void __maxnreg__(96) tc_gemm_kernel(const __grid_constant__ CUtensorM
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);     // warp-uniform
+    // everything above touched only shared memory / TMEM / kernel parameters: the next kernel of the stream may start its
+    // own prologue now, and this one must not read activations, weights or BN vectors before its predecessors are done
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -492,7 +496,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
     if (num_sms <= 0) return 2;
     int grid = num_sms * per_sm;
     if (grid > total) grid = total;
-    kern<<<grid, threads, smem, stream>>>(tmA, tmB, p);
+    // short launches (every CTA gets at most ~2 tiles) gain from overlapping their prologue with the previous kernel's tail
+    const bool pdl = total <= 2 * num_sms * per_sm;
+    if (check_cuda(launch_pdl(pdl, kern, dim3(grid), dim3(threads), smem, stream, tmA, tmB, p), "tc_gemm_kernel")) return 3;
     BPB_LAUNCH_CHECK("tc_gemm_kernel");
     return 0;
 }
