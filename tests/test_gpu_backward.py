@@ -614,4 +614,7 @@ def test_multi_lane_backward_equals_single_stream():
     print(msg)
     os.makedirs("gpurun_out", exist_ok=True)
     open("gpurun_out/lanes_report.txt", "w").write(msg + "\n")
-    assert cross < 3 * noise + 1e-4 and par_noise < 3 * noise + 1e-4, msg
+    # a lane / pool hazard hands a kernel the wrong buffer: errors of order 1 or NaN.  The floor keeps the check meaningful
+    # on a box where three serial runs happen to agree bit for bit (their measured spread is ~1.3e-2).
+    bound = max(3 * noise, 4e-2)
+    assert cross < bound and par_noise < bound and np.isfinite(cross), msg
