@@ -152,3 +152,38 @@ def test_rerank_rejects_cpu_inputs_without_a_device():
     d = np.zeros((2, 3), np.float32)
     with pytest.raises(RuntimeError):
         rerank.re_ranking(d, np.zeros((2, 2), np.float32), np.zeros((3, 3), np.float32))
+
+
+def test_ctypes_signatures_agree_with_the_header():
+    """Every prototype of include/bpbreid_sm100.h parsed and compared, argument by argument, with the ctypes table of
+    bpbreid_b200/_lib.py: pointers -> c_void_p, int -> c_int, int64_t -> c_int64, float -> c_float.  A drifted binding
+    would otherwise pass garbage across the ABI silently."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(_lib.__file__), "..", "include", "bpbreid_sm100.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", " ", hdr)
+    protos = re.findall(r"\b(?:int|int64_t|const char\*)\s+(bpb_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) >= 70
+    kind = {"c_void_p": "ptr", "c_int": "int", "c_long": "i64", "c_longlong": "i64", "c_float": "float"}
+    checked = 0
+    for name, args in protos:
+        if name not in _lib._SIGS:
+            continue
+        args = " ".join(args.split())
+        parts = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        want = []
+        for a in parts:
+            if "*" in a:
+                want.append("ptr")
+            elif re.match(r"(const\s+)?int64_t\b", a):
+                want.append("i64")
+            elif re.match(r"(const\s+)?float\b", a):
+                want.append("float")
+            elif re.match(r"(const\s+)?int\b", a):
+                want.append("int")
+            else:
+                raise AssertionError(f"{name}: unparsed parameter '{a}'")
+        got = [kind[t.__name__] for t in _lib._SIGS[name]]
+        assert got == want, f"{name}: header {want} vs ctypes {got}"
+        checked += 1
+    assert checked == len(_lib._SIGS)
