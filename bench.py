@@ -165,8 +165,28 @@ def time_cpu_port(batch, steps, warmup, h=256, w=128):
     return batch / dt, dt
 
 
+def workload_config(args, world):
+    """`config` of the JSON line -- identical for both arms (the reference arm runs a bounded sample of THIS workload)."""
+    h = args.height
+    per_gpu = args.batch if args.scaling == "weak" else args.batch // world
+    what = {"fwdloss": "forward + GiLt loss (3 ID-CE + part-averaged batch-hard triplet)",
+            "train": "forward + GiLt loss + analytic backward + Adam step"}[args.workload]
+    return {"workload": f"HRNet-W32 BPBreID K=5, {what}, train-mode BN, {h}x128, num_classes 751, random-init weights",
+            "per_gpu_batch": per_gpu, "global_batch": per_gpu * world,
+            "parallelism": f"dp{world}: batch sharded; one all-gather of the part embeddings, every rank mines its own "
+                           "anchor rows of the global pairwise matrix"
+                           + ("; bucketed NCCL all-reduce of the flat gradient" if args.workload == "train" else ""),
+            "l2": "working set >> 126 MB L2 and a 256 MB flush buffer is written between timed iterations",
+            "cuda_graph": True,
+            "head": "evaluated on the 4 un-concatenated HRNet branch maps (linear identity); the [N,1920,H/4,W/4] "
+                    "concat, which forward+loss never consumes, is not written"}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
+        return
+    if args.workload != "fwdloss":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm times forward + GiLt loss only"}), flush=True)
         return
     sample = 32
     warm = max(min(args.warmup, 3), 1)
@@ -175,11 +195,11 @@ def run_reference_arm(args, rank):
     line = {"impl": "reference", "metric": "images/sec fwd+loss", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"HRNet-W32 BPBreID K=5 fwd+GiLt, {args.height}x128, bounded sample of {sample} images/step "
-                                   "of the bs256 batch (CPU)", "per_gpu_batch": args.batch},
+            "config": workload_config(args, max(args.gpus, 1)),
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample}-image steps, fp32, oracle port of the reference (the Python reference "
-                                       "cannot travel to the GPU box)"},
+                             "sample": f"every step is a {sample}-image sample of the configured batch (same model / loss, fp32, "
+                                       "host cores; the 'l2' / 'cuda_graph' / 'head' notes of config describe the GPU arm), "
+                                       "oracle port of the reference (the Python reference cannot travel to the GPU box)"},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -679,22 +699,12 @@ def run_gpu_arm(args, rank, world):
     value = world * per_gpu / (ms_per_step * 1e-3)
     roof = roofline_probe(dev, peaks, per_gpu)
     cpu_ips, cpu_dt = time_cpu_port(32, 2, 1, h, 128) if not args.skip_cpu else (None, None)
-    what = {"fwdloss": "forward + GiLt loss (3 ID-CE + part-averaged batch-hard triplet)",
-            "train": "forward + GiLt loss + analytic backward + Adam step"}[args.workload]
     gf = GFLOP_PER_IMAGE.get(h, 10.68) * (3.0 if args.workload == "train" else 1.0)
     line = {
         "metric": "images/sec fwd+loss" if args.workload == "fwdloss" else "images/sec fwd+bwd+opt", "value": value,
         "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"HRNet-W32 BPBreID K=5, {what}, train-mode BN, {h}x128, num_classes 751, random-init weights",
-                   "per_gpu_batch": per_gpu, "global_batch": per_gpu * world,
-                   "parallelism": f"dp{world}: batch sharded; one all-gather of the part embeddings, every rank mines its own "
-                                  "anchor rows of the global pairwise matrix"
-                                  + ("; bucketed NCCL all-reduce of the flat gradient" if args.workload == "train" else ""),
-                   "l2": "working set >> 126 MB L2 and a 256 MB flush buffer is written between timed iterations",
-                   "cuda_graph": True, "loss": loss_val,
-                   "head": "evaluated on the 4 un-concatenated HRNet branch maps (linear identity); the [N,1920,H/4,W/4] "
-                           "concat, which forward+loss never consumes, is not written"},
+        "config": workload_config(args, world), "loss": loss_val,
         "clocks": clocks,
         "e2e": {"value": world * per_gpu * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4,
