@@ -32,12 +32,13 @@ def test_shard_bounds_keep_identities_together():
 class OracleCriterion:
     """GiLtLoss-shaped stub: same attributes / call signature, numbers from the numpy oracle."""
 
-    def __init__(self, weights):
+    def __init__(self, weights, use_visibility_scores=False):
         self.losses_weights = weights
+        self.use_visibility_scores = use_visibility_scores
 
     def __call__(self, emb, vis, ids, pids):
         n = lambda d: {k: v.numpy() for k, v in d.items()}  # noqa: E731
-        loss, summary = LO.gilt(n(emb), n(vis), n(ids), pids.numpy(), self.losses_weights, False, 0.3)
+        loss, summary = LO.gilt(n(emb), n(vis), n(ids), pids.numpy(), self.losses_weights, self.use_visibility_scores, 0.3)
         return torch.tensor(float(loss)), summary
 
 
@@ -49,11 +50,11 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, case="market", use_vis=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        c = GI.loss_case("market")
+        c = GI.loss_case(case)
         n = c["pids"].shape[0]
         lo, hi = D.shard_bounds(n, world, rank)
         sl = lambda d: {k: torch.from_numpy(v[lo:hi]) for k, v in d.items()}  # noqa: E731
@@ -63,8 +64,8 @@ def _worker(rank, world, port, q):
         g = D.all_gather_cat(emb["parts"])
         assert torch.equal(g, torch.from_numpy(c["emb"]["parts"]))
         gb = D.all_gather_cat(vis["parts"])
-        assert gb.dtype == torch.bool and torch.equal(gb, torch.from_numpy(c["vis"]["parts"]))
-        loss, summary = D.distributed_gilt(OracleCriterion(c["weights"]), emb, vis, ids, pids)
+        assert gb.dtype == torch.from_numpy(c["vis"]["parts"]).dtype and torch.equal(gb, torch.from_numpy(c["vis"]["parts"]))
+        loss, summary = D.distributed_gilt(OracleCriterion(c["weights"], use_vis), emb, vis, ids, pids)
         q.put((rank, float(loss), float(summary["parts"]["t"]), float(summary["globl"]["c"])))
     finally:
         dist.destroy_process_group()
@@ -90,3 +91,32 @@ def test_distributed_gilt_equals_whole_batch_gilt_world2():
     lo, hi = D.shard_bounds(c["pids"].shape[0], world, 0)
     local = LO.part_averaged_triplet(c["emb"]["parts"][lo:hi], c["pids"][lo:hi], 0.3)
     assert abs(float(local[0]) - summ["parts"]["t"]) > 1e-4
+
+
+@pytest.mark.parametrize("case", ["vis_bool", "vis_float"])
+def test_distributed_gilt_with_visibility_scores_normalises_globally(case):
+    """with visibility scores the identity terms are weighted means (bool: invisible rows dropped; float:
+    sum(w*CE)/sum|w|, cross_entropy_loss.py:50-53).  Ranks see different weight totals, so the mean of the local means is
+    NOT the whole-batch value: numerator and denominator must be reduced separately."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, case, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    c = GI.loss_case(case)
+    whole, _ = LO.gilt(c["emb"], c["vis"], c["ids"], c["pids"], c["weights"], True, 0.3)
+    for rank, loss, _, _ in res:
+        assert abs(loss - float(whole)) < 1e-5 * abs(float(whole)), (rank, loss, float(whole))
+    # the naive average of per-shard losses differs measurably
+    lo, hi = D.shard_bounds(c["pids"].shape[0], world, 0)
+    sl = lambda d, a, b: {k: v[a:b] for k, v in d.items()}  # noqa: E731
+    only_id = {k: {"id": v["id"], "tr": 0.0} for k, v in c["weights"].items()}
+    halves = [LO.gilt(sl(c["emb"], a, b), sl(c["vis"], a, b), sl(c["ids"], a, b), c["pids"][a:b], only_id, True, 0.3)[0]
+              for a, b in ((lo, hi), (hi, c["pids"].shape[0]))]
+    whole_id = LO.gilt(c["emb"], c["vis"], c["ids"], c["pids"], only_id, True, 0.3)[0]
+    assert abs(float(np.mean(halves)) - float(whole_id)) > 1e-6
